@@ -1,0 +1,232 @@
+"""ctypes binding of libgraphrole_b200.so (C-ABI declared in include/graphrole_b200.h).
+
+This module is deliberately thin: argument marshalling and error translation only.  There is
+no CPU fallback anywhere in the package -- if the shared library is missing or the device is
+not sm_100, calls raise.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libgraphrole_b200.so')
+
+GR_OK = 0
+GR_ERR_INVALID_ARGUMENT = 1
+GR_ERR_INVALID_GRAPH = 2
+GR_ERR_CUDA = 3
+GR_ERR_UNSUPPORTED_DEVICE = 4
+GR_ERR_OUT_OF_MEMORY = 5
+
+# every symbol include/graphrole_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    'gr_last_error': (c_char_p, []),
+    'gr_version': (c_char_p, []),
+    'gr_kernel_launch_count': (c_int64, []),
+    'gr_csr_create': (c_int, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                              c_int, c_int]),
+    'gr_csr_destroy': (c_int, [c_void_p]),
+    'gr_csr_info': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                            POINTER(c_int64), POINTER(c_int64)]),
+    'gr_refex_aggregate_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
+                                       c_void_p, c_void_p, c_int64, c_void_p]),
+    'gr_refex_levels_host_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                         c_void_p, c_void_p]),
+    'gr_nmf_create': (c_int, [POINTER(c_void_p), c_int64, c_int32, c_int32, c_int]),
+    'gr_nmf_destroy': (c_int, [c_void_p]),
+    'gr_nmf_mu_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_double,
+                              c_int32, c_int32, POINTER(c_int32), POINTER(c_double), c_void_p]),
+    'gr_nmf_error_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 POINTER(c_double), c_void_p]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA library is missing, failed to load, or a call into it failed."""
+
+    def __init__(self, message, code=None):
+        super().__init__(message)
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libgraphrole_b200.so and bind every declared symbol.  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; '
+            f'g.build()"` (nvcc, sm_100a). graphrole_b200 has no CPU fallback.')
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise NativeLibraryError(f'cannot load {LIB_PATH}: {exc}') from exc
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise NativeLibraryError(f'{LIB_PATH} does not export {name}') from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    """Translate a non-zero status into the exception class the reference's callers expect."""
+    if code == GR_OK:
+        return
+    msg = (load().gr_last_error() or b'').decode('utf-8', 'replace')
+    text = f'{what}: {msg} (status {code})'
+    if code in (GR_ERR_INVALID_ARGUMENT, GR_ERR_INVALID_GRAPH):
+        raise ValueError(text)
+    if code == GR_ERR_OUT_OF_MEMORY:
+        raise MemoryError(text)
+    raise NativeLibraryError(text, code)
+
+
+def launch_count():
+    return int(load().gr_kernel_launch_count())
+
+
+def version():
+    return load().gr_version().decode()
+
+
+def _stream_ptr(stream):
+    """cudaStream_t of a torch stream (None = torch's current stream)."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return c_void_p(stream.cuda_stream)
+
+
+class CsrHandle:
+    """Owner of a gr_csr_t*.  Keeps the rowptr/colidx tensors alive (the library does not copy)."""
+
+    def __init__(self, rowptr, colidx, n_cols=None, validate=True):
+        import torch
+        lib = load()
+        if not (rowptr.is_cuda and colidx.is_cuda):
+            raise ValueError('rowptr/colidx must be CUDA tensors')
+        if rowptr.dtype != torch.int64 or colidx.dtype != torch.int32:
+            raise ValueError('rowptr must be int64 and colidx int32')
+        self.rowptr = rowptr.contiguous()
+        self.colidx = colidx.contiguous()
+        self.n_rows = self.rowptr.numel() - 1
+        self.n_cols = int(self.n_rows if n_cols is None else n_cols)
+        self.nnz = self.colidx.numel()
+        self.device = self.rowptr.device
+        handle = c_void_p()
+        # the library reads rowptr with a blocking copy on the legacy stream: make sure the
+        # producer stream is done
+        torch.cuda.current_stream(self.device).synchronize()
+        check(lib.gr_csr_create(byref(handle), self.n_rows, self.n_cols, self.nnz,
+                                c_void_p(self.rowptr.data_ptr()),
+                                c_void_p(self.colidx.data_ptr()),
+                                self.device.index or 0, 1 if validate else 0),
+              'gr_csr_create')
+        self._handle = handle
+
+    def info(self):
+        vals = [c_int64() for _ in range(5)]
+        check(load().gr_csr_info(self._handle, *[byref(v) for v in vals]), 'gr_csr_info')
+        keys = ('n_rows', 'n_cols', 'nnz', 'n_hub_rows', 'n_hub_segments')
+        return {k: int(v.value) for k, v in zip(keys, vals)}
+
+    def aggregate(self, X, out=None, row_lo=0, row_hi=None, stream=None):
+        """One recursion level.  X: [n_cols, d] fp32 (row stride free, unit column stride).
+
+        Returns `out` of shape [row_hi - row_lo, 2*d]: columns [0, d) = sum, [d, 2d) = mean,
+        the reference's agg-major order (graphrole/features/extract.py:158-162).
+        """
+        import torch
+        if X.dtype != torch.float32 or not X.is_cuda or X.dim() != 2:
+            raise ValueError('X must be a 2-D float32 CUDA tensor')
+        if X.stride(1) != 1 and X.shape[1] > 1:
+            raise ValueError('X must have unit column stride')
+        if X.shape[0] != self.n_cols:
+            raise ValueError(f'X has {X.shape[0]} rows, graph addresses {self.n_cols}')
+        d = X.shape[1]
+        row_hi = self.n_rows if row_hi is None else row_hi
+        rows = row_hi - row_lo
+        if out is None:
+            out = torch.empty((rows, 2 * d), dtype=torch.float32, device=X.device)
+        if out.shape != (rows, 2 * d) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f'out must be a contiguous float32 [{rows}, {2 * d}] tensor')
+        ldx = X.stride(0) if X.shape[0] > 1 else max(d, X.stride(0))
+        # out pointers are addressed by handle-local row number: rebase to row 0
+        base = out.data_ptr() - row_lo * 2 * d * 4
+        check(load().gr_refex_aggregate_f32(
+            self._handle, c_void_p(X.data_ptr()), ldx, d, row_lo, row_hi,
+            c_void_p(base), c_void_p(base + d * 4), 2 * d, _stream_ptr(stream)),
+            'gr_refex_aggregate_f32')
+        return out
+
+    def aggregate_into(self, X, out_sum, out_mean, row_lo=0, row_hi=None, stream=None):
+        """Low-level form: separate [rows, d] outputs sharing one row stride (either may be
+        None).  Used by the sharded path to write mean rows straight into the next level's
+        full input matrix."""
+        import torch
+        if X.dtype != torch.float32 or not X.is_cuda or X.dim() != 2 or X.stride(1) != 1:
+            raise ValueError('X must be a 2-D float32 CUDA tensor with unit column stride')
+        if X.shape[0] != self.n_cols:
+            raise ValueError(f'X has {X.shape[0]} rows, graph addresses {self.n_cols}')
+        d = X.shape[1]
+        row_hi = self.n_rows if row_hi is None else row_hi
+        rows = row_hi - row_lo
+        ldo = None
+        ptrs = []
+        for t in (out_sum, out_mean):
+            if t is None:
+                ptrs.append(c_void_p(0))
+                continue
+            if (t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != (rows, d)
+                    or (d > 1 and t.stride(1) != 1)):
+                raise ValueError(f'outputs must be float32 CUDA [{rows}, {d}] row-major')
+            ld = t.stride(0) if rows > 1 else d
+            if ldo is not None and ld != ldo:
+                raise ValueError('out_sum and out_mean must share one row stride')
+            ldo = ld
+            ptrs.append(c_void_p(t.data_ptr() - row_lo * ld * 4))
+        if ldo is None:
+            raise ValueError('at least one output is required')
+        check(load().gr_refex_aggregate_f32(
+            self._handle, c_void_p(X.data_ptr()), X.stride(0) if X.shape[0] > 1 else d, d,
+            row_lo, row_hi, ptrs[0], ptrs[1], ldo, _stream_ptr(stream)),
+            'gr_refex_aggregate_f32')
+
+    def levels_host(self, X_host, levels, recurse_on='mean', out_host=None, stream=None):
+        """Host-buffer entry point: H2D of X, `levels` recursion levels, D2H of every level."""
+        import torch
+        if X_host.dtype != torch.float32 or X_host.is_cuda or X_host.dim() != 2:
+            raise ValueError('X_host must be a 2-D float32 CPU tensor')
+        if X_host.shape[0] != self.n_cols or X_host.stride(1) != 1:
+            raise ValueError('X_host must be [n_cols, d] with unit column stride')
+        d = X_host.shape[1]
+        if out_host is None:
+            out_host = torch.empty((levels, self.n_rows, 2 * d), dtype=torch.float32,
+                                   pin_memory=True)
+        if tuple(out_host.shape) != (levels, self.n_rows, 2 * d) or not out_host.is_contiguous():
+            raise ValueError('out_host must be contiguous [levels, n_rows, 2*d]')
+        with torch.cuda.device(self.device):
+            check(load().gr_refex_levels_host_f32(
+                self._handle, c_void_p(X_host.data_ptr()), X_host.stride(0), d, levels,
+                {'sum': 0, 'mean': 1}[recurse_on], c_void_p(out_host.data_ptr()),
+                _stream_ptr(stream)), 'gr_refex_levels_host_f32')
+        return out_host
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().gr_csr_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

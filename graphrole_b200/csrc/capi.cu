@@ -1,0 +1,172 @@
+// Library-level entry points and the CSR graph handle (include/graphrole_b200.h).
+//
+// gr_csr_create is the native form of the reference's graph plugin calls
+// graph.get_nodes()/graph.get_neighbors(node) (graphrole/graph/interface/base.py:58-69,
+// interface/networkx.py:36-46): the host side (graphrole_b200/graph) flattens them once into
+// rowptr/colidx and every recursion level reuses the handle.
+
+#include <algorithm>
+
+#include "csr_handle.cuh"
+
+using namespace gr;
+
+extern "C" const char* gr_last_error(void) { return tls_error_buffer(); }
+
+extern "C" const char* gr_version(void) { return "graphrole_b200 0.1.0 sm_100a"; }
+
+extern "C" int64_t gr_kernel_launch_count(void) {
+    return launch_counter().load(std::memory_order_relaxed);
+}
+
+namespace {
+
+// Range check of colidx: counts entries outside [0, n_cols).
+__global__ void __launch_bounds__(256)
+colidx_range_kernel(const int32_t* __restrict__ colidx, int64_t nnz, int64_t n_cols,
+                    unsigned long long* __restrict__ bad) {
+    unsigned long long local = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t c = __ldcs(colidx + i);
+        local += (c < 0 || (int64_t)c >= n_cols) ? 1ull : 0ull;
+    }
+    local = __reduce_add_sync(0xffffffffu, (unsigned)local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(bad, local);
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return GR_OK;
+    GR_CUDA_TRY(cudaMalloc(dst, src.size() * sizeof(T)));
+    GR_CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GR_OK;
+}
+
+}  // namespace
+
+extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                             const int64_t* rowptr_dev, const int32_t* colidx_dev,
+                             int device, int validate) {
+    GR_REQUIRE(out != nullptr, "gr_csr_create: out is NULL");
+    *out = nullptr;
+    GR_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "gr_csr_create: negative size");
+    GR_REQUIRE(n_cols <= (int64_t)INT32_MAX, "gr_csr_create: n_cols exceeds int32 colidx range");
+    GR_REQUIRE(rowptr_dev != nullptr, "gr_csr_create: rowptr is NULL");
+    GR_REQUIRE(nnz == 0 || colidx_dev != nullptr, "gr_csr_create: colidx is NULL with nnz > 0");
+    GR_REQUIRE((reinterpret_cast<uintptr_t>(rowptr_dev) & 7u) == 0 &&
+               (reinterpret_cast<uintptr_t>(colidx_dev) & 3u) == 0,
+               "gr_csr_create: rowptr must be 8-byte and colidx 4-byte aligned");
+
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "gr_csr_create: cannot select device %d", device);
+    if (int rc = require_sm100(device)) return rc;
+
+    // rowptr is 8(n+1) bytes (80 MB at 10 M nodes): validate and find hub rows on the host.
+    std::vector<int64_t> rp((size_t)n_rows + 1);
+    GR_CUDA_TRY(cudaMemcpy(rp.data(), rowptr_dev, rp.size() * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost));
+    if (rp[0] != 0)
+        return fail(GR_ERR_INVALID_GRAPH, "rowptr[0] = %lld, expected 0", (long long)rp[0]);
+    if (rp[(size_t)n_rows] != nnz)
+        return fail(GR_ERR_INVALID_GRAPH, "rowptr[n_rows] = %lld, expected nnz = %lld",
+                    (long long)rp[(size_t)n_rows], (long long)nnz);
+
+    gr_csr* g = new (std::nothrow) gr_csr();
+    if (!g) return fail(GR_ERR_OUT_OF_MEMORY, "gr_csr_create: host allocation failed");
+    g->device = device;
+    g->n_rows = n_rows;
+    g->n_cols = n_cols;
+    g->nnz = nnz;
+    g->rowptr = rowptr_dev;
+    g->colidx = colidx_dev;
+
+    std::vector<int64_t> seg_begin, seg_end;
+    g->h_hub_seg_first.push_back(0);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t b = rp[(size_t)r], e = rp[(size_t)r + 1];
+        if (e < b) {
+            delete g;
+            return fail(GR_ERR_INVALID_GRAPH, "rowptr decreases at row %lld (%lld -> %lld)",
+                        (long long)r, (long long)b, (long long)e);
+        }
+        if (e - b > kHubThreshold) {
+            g->h_hub_row.push_back(r);
+            for (int64_t s = b; s < e; s += kHubSegment) {
+                seg_begin.push_back(s);
+                seg_end.push_back(std::min(e, s + kHubSegment));
+            }
+            g->h_hub_seg_first.push_back((int64_t)seg_begin.size());
+        }
+    }
+    g->n_hub_rows = (int64_t)g->h_hub_row.size();
+    g->n_segments = (int64_t)seg_begin.size();
+
+    int rc = GR_OK;
+    if ((rc = upload(&g->d_hub_row, g->h_hub_row)) ||
+        (rc = upload(&g->d_hub_seg_first, g->h_hub_seg_first)) ||
+        (rc = upload(&g->d_seg_begin, seg_begin)) || (rc = upload(&g->d_seg_end, seg_end))) {
+        gr_csr_destroy(g);
+        return rc;
+    }
+
+    if (validate && nnz > 0) {
+        unsigned long long* d_bad = nullptr;
+        unsigned long long h_bad = 0;
+        cudaError_t e = cudaMalloc(&d_bad, sizeof(*d_bad));
+        if (e == cudaSuccess) e = cudaMemset(d_bad, 0, sizeof(*d_bad));
+        if (e == cudaSuccess) {
+            const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(nnz, 256), 148 * 16);
+            colidx_range_kernel<<<blocks, 256>>>(colidx_dev, nnz, n_cols, d_bad);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpy(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        if (e != cudaSuccess) {
+            gr_csr_destroy(g);
+            return fail(GR_ERR_CUDA, "colidx validation failed: %s", cudaGetErrorString(e));
+        }
+        if (h_bad) {
+            gr_csr_destroy(g);
+            return fail(GR_ERR_INVALID_GRAPH, "%llu colidx entries outside [0, %lld)", h_bad,
+                        (long long)n_cols);
+        }
+    }
+
+    *out = g;
+    return GR_OK;
+}
+
+extern "C" int gr_csr_destroy(gr_csr_t* g) {
+    if (!g) return GR_OK;
+    DeviceGuard guard(g->device);
+    cudaFree(g->d_hub_row);
+    cudaFree(g->d_hub_seg_first);
+    cudaFree(g->d_seg_begin);
+    cudaFree(g->d_seg_end);
+    cudaFree(g->d_partial);
+    cudaFree(g->d_stage_x);
+    cudaFree(g->d_stage_out[0]);
+    cudaFree(g->d_stage_out[1]);
+    if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (g->ev_level[i]) cudaEventDestroy(g->ev_level[i]);
+        if (g->ev_copied[i]) cudaEventDestroy(g->ev_copied[i]);
+    }
+    delete g;
+    return GR_OK;
+}
+
+extern "C" int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                           int64_t* n_hub_rows, int64_t* n_hub_segments) {
+    GR_REQUIRE(g != nullptr, "gr_csr_info: handle is NULL");
+    if (n_rows) *n_rows = g->n_rows;
+    if (n_cols) *n_cols = g->n_cols;
+    if (nnz) *nnz = g->nnz;
+    if (n_hub_rows) *n_hub_rows = g->n_hub_rows;
+    if (n_hub_segments) *n_hub_segments = g->n_segments;
+    return GR_OK;
+}

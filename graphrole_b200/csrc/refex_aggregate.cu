@@ -1,0 +1,418 @@
+// Path A: one ReFeX recursion level as a CSR gather-reduce (fused sum + mean) for sm_100a.
+//
+// Replaces the per-node pandas chain of RecursiveFeatureExtractor._get_next_features
+// (graphrole/features/extract.py:105-118): reindex(neighbours) -> agg([sum, mean]) ->
+// fillna(0), i.e. S = A.X and M = S / outdeg with A the binary out-adjacency.
+//
+// The kernel is HBM bound (0.25 flop/byte): everything below is about keeping many 16-byte
+// row-gather requests in flight per SM and not moving a byte twice.
+//   * a warp owns `rows_per_warp` CONSECUTIVE rows, so its colidx span is one contiguous
+//     stream, read in 128-byte-aligned chunks of 32 indices with one chunk of prefetch, and
+//     its rowptr entries are one coalesced load; only the X-row gathers are dependent loads;
+//   * a feature row (d floats) is covered by LPR = d/4 lanes with one float4 each; the
+//     32/LPR lane groups of the warp take different neighbours and every group keeps U
+//     independent loads (and U independent fp32 accumulators) in flight;
+//   * colidx and the outputs are touched once and use streaming (evict-first) accesses so L2
+//     is left to the gathered rows, which is where power-law graphs have reuse;
+//   * rows longer than kHubThreshold arcs are cut into kHubSegment-arc segments handled by
+//     the leading CTAs of the same launch; a small second kernel adds a row's partials in
+//     fp64 in segment order (bitwise reproducible, no float atomics).
+
+#include <algorithm>
+
+#include "csr_handle.cuh"
+
+using namespace gr;
+
+namespace {
+
+constexpr int kWarps = 8;  // 256 threads per CTA
+constexpr unsigned kFull = 0xffffffffu;
+
+struct RefexArgs {
+    const int64_t* __restrict__ rowptr;
+    const int32_t* __restrict__ colidx;
+    const float* __restrict__ X;
+    int64_t ldx;
+    int32_t d;
+    int64_t row_lo, row_hi;
+    float* __restrict__ out_sum;
+    float* __restrict__ out_mean;
+    int64_t ldo;
+    const int64_t* __restrict__ seg_begin;
+    const int64_t* __restrict__ seg_end;
+    int64_t seg_lo, seg_hi;
+    float* __restrict__ partial;  // [n_segments, d], indexed by handle-global segment id
+    int64_t n_seg_blocks;         // leading CTAs (blockIdx.x) that reduce hub segments
+    int32_t rows_per_warp;
+};
+
+// ---- vector helpers -------------------------------------------------------------------
+template <int VW>
+__device__ __forceinline__ void load_row(float (&v)[VW], const float* p, bool ok);
+
+template <>
+__device__ __forceinline__ void load_row<4>(float (&v)[4], const float* p, bool ok) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load_row<1>(float (&v)[1], const float* p, bool ok) {
+    v[0] = ok ? __ldg(p) : 0.f;
+}
+
+template <int VW>
+__device__ __forceinline__ void store_stream(float* p, const float (&v)[VW], float scale);
+
+template <>
+__device__ __forceinline__ void store_stream<4>(float* p, const float (&v)[4], float scale) {
+    __stcs(reinterpret_cast<float4*>(p),
+           make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale));
+}
+template <>
+__device__ __forceinline__ void store_stream<1>(float* p, const float (&v)[1], float scale) {
+    __stcs(p, v[0] * scale);
+}
+
+// ---- the warp's view of its contiguous colidx span --------------------------------------
+struct ArcStream {
+    const int32_t* __restrict__ colidx;
+    int64_t limit;  // positions >= limit are never dereferenced
+    int64_t base;   // 32-aligned position of the chunk held in `cur`
+    int32_t cur, nxt;
+
+    __device__ __forceinline__ int32_t fetch(int64_t p) const {
+        return p < limit ? __ldcs(colidx + p) : 0;
+    }
+    __device__ __forceinline__ void open(int64_t pos, int lane) {
+        base = pos & ~int64_t(31);
+        cur = fetch(base + lane);
+        nxt = fetch(base + 32 + lane);
+    }
+    // make `pos` fall inside the current chunk (warp-uniform control flow)
+    __device__ __forceinline__ void seek(int64_t pos, int lane) {
+        if (pos < base + 32) return;
+        if (pos < base + 64) {
+            cur = nxt;
+            base += 32;
+            nxt = fetch(base + 32 + lane);
+        } else {
+            open(pos, lane);
+        }
+    }
+};
+
+// Sum of X[colidx[k], col..col+VW) over k in [beg, end); result replicated in every lane group.
+template <int LPR, int VW, int U>
+__device__ __forceinline__ void reduce_arcs(ArcStream& s, int64_t beg, int64_t end,
+                                            const float* __restrict__ xcol, int64_t ldx,
+                                            bool col_ok, int lane, float (&total)[VW]) {
+    constexpr int G = 32 / LPR;
+    const int grp = lane / LPR;
+    float acc[U][VW];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < VW; ++c) acc[u][c] = 0.f;
+
+    int64_t k = beg;
+    while (k < end) {
+        s.seek(k, lane);
+        const int off = (int)(k - s.base);
+        const int cnt = (int)min(end - k, (int64_t)(32 - off));
+        for (int t = 0; t < cnt; t += G * U) {
+            float v[U][VW];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = t + u * G + grp;
+                const int32_t idx = __shfl_sync(kFull, s.cur, (off + kk) & 31);
+                load_row<VW>(v[u], xcol + (int64_t)idx * ldx, col_ok && kk < cnt);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < VW; ++c) acc[u][c] += v[u][c];
+        }
+        k += cnt;
+    }
+    // pairwise combine of the U accumulators, then of the lane groups
+#pragma unroll
+    for (int step = 1; step < U; step <<= 1)
+#pragma unroll
+        for (int u = 0; u + step < U; u += 2 * step)
+#pragma unroll
+            for (int c = 0; c < VW; ++c) acc[u][c] += acc[u + step][c];
+#pragma unroll
+    for (int c = 0; c < VW; ++c) {
+        float t = acc[0][c];
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) t += __shfl_xor_sync(kFull, t, o);
+        total[c] = t;
+    }
+}
+
+template <int LPR, int VW, int U>
+__global__ void __launch_bounds__(kWarps * 32)
+refex_gather_kernel(const RefexArgs a) {
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const int col = ((int)blockIdx.y * LPR + sub) * VW;
+    const bool col_ok = col < a.d;
+    const float* xcol = a.X + col;
+
+    ArcStream s;
+    s.colidx = a.colidx;
+
+    if ((int64_t)blockIdx.x < a.n_seg_blocks) {
+        // ---- hub segment: one warp reduces kHubSegment arcs of a long row into a partial
+        const int64_t seg = a.seg_lo + (int64_t)blockIdx.x * kWarps + warp;
+        if (seg >= a.seg_hi) return;
+        const int64_t beg = __ldg(a.seg_begin + seg), end = __ldg(a.seg_end + seg);
+        s.limit = end;
+        s.open(beg, lane);
+        float tot[VW];
+        reduce_arcs<LPR, VW, U>(s, beg, end, xcol, a.ldx, col_ok, lane, tot);
+        if (col_ok && grp == 0) store_stream<VW>(a.partial + seg * a.d + col, tot, 1.f);
+        return;
+    }
+
+    // ---- ordinary rows: rows_per_warp consecutive rows per warp
+    const int64_t rb = (int64_t)blockIdx.x - a.n_seg_blocks;
+    const int64_t first = a.row_lo + (rb * kWarps + warp) * a.rows_per_warp;
+    if (first >= a.row_hi) return;
+    const int nrows = (int)min((int64_t)a.rows_per_warp, a.row_hi - first);
+    const int64_t rp = lane <= nrows ? __ldg(a.rowptr + first + lane) : 0;
+    s.limit = __shfl_sync(kFull, rp, nrows);
+    s.open(__shfl_sync(kFull, rp, 0), lane);
+
+    for (int r = 0; r < nrows; ++r) {
+        const int64_t beg = __shfl_sync(kFull, rp, r);
+        const int64_t end = __shfl_sync(kFull, rp, r + 1);
+        const int64_t deg = end - beg;
+        if (deg > kHubThreshold) continue;  // produced by segment warps + hub_fixup_kernel
+        float tot[VW];
+        reduce_arcs<LPR, VW, U>(s, beg, end, xcol, a.ldx, col_ok, lane, tot);
+        if (!col_ok) continue;
+        const int64_t o = (first + r) * a.ldo + col;
+        // lane group 0 writes the sum block, group 1 (or the same lanes when LPR == 32) the mean
+        if (a.out_sum && grp == 0) store_stream<VW>(a.out_sum + o, tot, 1.f);
+        if (a.out_mean && grp == (G >= 2 ? 1 : 0)) {
+            float m[VW];
+#pragma unroll
+            for (int c = 0; c < VW; ++c) m[c] = deg > 0 ? tot[c] / (float)deg : 0.f;
+            store_stream<VW>(a.out_mean + o, m, 1.f);
+        }
+    }
+}
+
+// One warp per hub row: add the row's segment partials in fp64, in segment order.
+__global__ void __launch_bounds__(kWarps * 32)
+hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict__ hub_seg_first,
+                 const int64_t* __restrict__ rowptr, int64_t hub_lo, int64_t hub_hi,
+                 const float* __restrict__ partial, int32_t d, float* __restrict__ out_sum,
+                 float* __restrict__ out_mean, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t h = hub_lo + (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (h >= hub_hi) return;
+    const int64_t row = hub_row[h];
+    const int64_t s0 = hub_seg_first[h], s1 = hub_seg_first[h + 1];
+    const double deg = (double)(rowptr[row + 1] - rowptr[row]);
+    for (int c = lane; c < d; c += 32) {
+        double acc = 0.0;
+        for (int64_t s = s0; s < s1; ++s) acc += (double)partial[s * d + c];
+        if (out_sum) out_sum[row * ldo + c] = (float)acc;
+        if (out_mean) out_mean[row * ldo + c] = (float)(acc / deg);
+    }
+}
+
+// ---- launch plumbing --------------------------------------------------------------------
+template <int LPR, int VW, int U>
+cudaError_t launch_gather(const RefexArgs& a, dim3 grid, cudaStream_t st) {
+    refex_gather_kernel<LPR, VW, U><<<grid, kWarps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int VW, int U>
+cudaError_t dispatch_lpr(int lpr, const RefexArgs& a, dim3 grid, cudaStream_t st) {
+    switch (lpr) {
+        case 1: return launch_gather<1, VW, U>(a, grid, st);
+        case 2: return launch_gather<2, VW, U>(a, grid, st);
+        case 4: return launch_gather<4, VW, U>(a, grid, st);
+        case 8: return launch_gather<8, VW, U>(a, grid, st);
+        case 16: return launch_gather<16, VW, U>(a, grid, st);
+        default: return launch_gather<32, VW, U>(a, grid, st);
+    }
+}
+
+int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    const int v = atoi(s);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+int ensure_floats(float** buf, size_t* have, size_t want) {
+    if (*have >= want) return GR_OK;
+    if (*buf) {
+        GR_CUDA_TRY(cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    GR_CUDA_TRY(cudaMalloc(buf, want * sizeof(float)));
+    *have = want;
+    return GR_OK;
+}
+
+}  // namespace
+
+extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, int32_t d,
+                                      int64_t row_lo, int64_t row_hi, float* out_sum,
+                                      float* out_mean, int64_t ldo, void* stream) {
+    GR_REQUIRE(g != nullptr, "gr_refex_aggregate_f32: handle is NULL");
+    GR_REQUIRE(d >= 1, "gr_refex_aggregate_f32: d = %d, need d >= 1", d);
+    GR_REQUIRE(X != nullptr, "gr_refex_aggregate_f32: X is NULL");
+    GR_REQUIRE(out_sum != nullptr || out_mean != nullptr,
+               "gr_refex_aggregate_f32: both outputs are NULL");
+    GR_REQUIRE(ldx >= d && ldo >= d, "gr_refex_aggregate_f32: ldx = %lld / ldo = %lld < d = %d",
+               (long long)ldx, (long long)ldo, d);
+    GR_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= g->n_rows,
+               "gr_refex_aggregate_f32: row range [%lld, %lld) outside [0, %lld)",
+               (long long)row_lo, (long long)row_hi, (long long)g->n_rows);
+    if (row_lo == row_hi) return GR_OK;
+
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", g->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // hub rows / segments intersecting the row range
+    const auto hb = std::lower_bound(g->h_hub_row.begin(), g->h_hub_row.end(), row_lo);
+    const auto he = std::lower_bound(g->h_hub_row.begin(), g->h_hub_row.end(), row_hi);
+    const int64_t hub_lo = hb - g->h_hub_row.begin(), hub_hi = he - g->h_hub_row.begin();
+    const int64_t seg_lo = g->h_hub_seg_first[(size_t)hub_lo];
+    const int64_t seg_hi = g->h_hub_seg_first[(size_t)hub_hi];
+    if (seg_hi > seg_lo)
+        if (int rc = ensure_floats(&g->d_partial, &g->partial_floats,
+                                   (size_t)g->n_segments * (size_t)d))
+            return rc;
+
+    RefexArgs a;
+    a.rowptr = g->rowptr;
+    a.colidx = g->colidx;
+    a.X = X;
+    a.ldx = ldx;
+    a.d = d;
+    a.row_lo = row_lo;
+    a.row_hi = row_hi;
+    a.out_sum = out_sum;
+    a.out_mean = out_mean;
+    a.ldo = ldo;
+    a.seg_begin = g->d_seg_begin;
+    a.seg_end = g->d_seg_end;
+    a.seg_lo = seg_lo;
+    a.seg_hi = seg_hi;
+    a.partial = g->d_partial;
+    a.n_seg_blocks = ceil_div<int64_t>(seg_hi - seg_lo, kWarps);
+    a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", 8, 1, 31);
+
+    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) &&
+                      (!out_sum || aligned16(out_sum)) && (!out_mean || aligned16(out_mean));
+    const int vw = vec4 ? 4 : 1;
+    const int units = ceil_div<int>(d, vw);  // lanes needed to cover one feature row
+    int lpr = vec4 ? 1 : 4;
+    while (lpr < units && lpr < 32) lpr <<= 1;
+    const int col_tiles = ceil_div<int>(units, lpr);
+
+    const int64_t row_blocks =
+        ceil_div<int64_t>(row_hi - row_lo, (int64_t)kWarps * a.rows_per_warp);
+    GR_REQUIRE(row_blocks + a.n_seg_blocks < (int64_t)INT32_MAX && col_tiles <= 65535,
+               "gr_refex_aggregate_f32: grid too large");
+    dim3 grid((unsigned)(row_blocks + a.n_seg_blocks), (unsigned)col_tiles, 1);
+
+    cudaError_t e;
+    if (vec4) {
+        switch (env_int("GR_REFEX_UNROLL", 4, 1, 8)) {
+            case 1: e = dispatch_lpr<4, 1>(lpr, a, grid, st); break;
+            case 2: e = dispatch_lpr<4, 2>(lpr, a, grid, st); break;
+            case 8: e = dispatch_lpr<4, 8>(lpr, a, grid, st); break;
+            default: e = dispatch_lpr<4, 4>(lpr, a, grid, st); break;
+        }
+    } else {
+        e = dispatch_lpr<1, 4>(lpr, a, grid, st);
+    }
+    count_launch();
+    if (e != cudaSuccess)
+        return fail(GR_ERR_CUDA, "refex_gather_kernel launch failed: %s", cudaGetErrorString(e));
+
+    if (hub_hi > hub_lo) {
+        hub_fixup_kernel<<<(unsigned)ceil_div<int64_t>(hub_hi - hub_lo, kWarps), kWarps * 32, 0,
+                           st>>>(g->d_hub_row, g->d_hub_seg_first, g->rowptr, hub_lo, hub_hi,
+                                 g->d_partial, d, out_sum, out_mean, ldo);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return fail(GR_ERR_CUDA, "hub_fixup_kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    return GR_OK;
+}
+
+extern "C" int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,
+                                        int32_t levels, int32_t recurse_on, float* out_host,
+                                        void* stream) {
+    GR_REQUIRE(g != nullptr, "gr_refex_levels_host_f32: handle is NULL");
+    GR_REQUIRE(X_host != nullptr && out_host != nullptr, "gr_refex_levels_host_f32: NULL buffer");
+    GR_REQUIRE(d >= 1 && ldx >= d && levels >= 1, "gr_refex_levels_host_f32: bad d/ldx/levels");
+    GR_REQUIRE(recurse_on == 0 || recurse_on == 1, "recurse_on must be 0 (sum) or 1 (mean)");
+    GR_REQUIRE(levels == 1 || g->n_rows == g->n_cols,
+               "gr_refex_levels_host_f32: levels > 1 needs an unsharded graph "
+               "(n_rows = %lld, n_cols = %lld)", (long long)g->n_rows, (long long)g->n_cols);
+
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", g->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const size_t out_floats = (size_t)g->n_rows * 2 * (size_t)d;
+    if (int rc = ensure_floats(&g->d_stage_x, &g->stage_x_floats, (size_t)g->n_cols * d)) return rc;
+    if (g->stage_out_floats < out_floats) {
+        for (int i = 0; i < 2; ++i) {
+            size_t have = g->stage_out_floats;
+            if (int rc = ensure_floats(&g->d_stage_out[i], &have, out_floats)) return rc;
+        }
+        g->stage_out_floats = out_floats;
+    }
+    if (!g->copy_stream) {
+        GR_CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GR_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_level[i], cudaEventDisableTiming));
+            GR_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+
+    GR_CUDA_TRY(cudaMemcpy2DAsync(g->d_stage_x, (size_t)d * sizeof(float), X_host,
+                                  (size_t)ldx * sizeof(float), (size_t)d * sizeof(float),
+                                  (size_t)g->n_cols, cudaMemcpyHostToDevice, st));
+    for (int l = 0; l < levels; ++l) {
+        const int slot = l & 1;
+        const float* in = l == 0 ? g->d_stage_x
+                                 : g->d_stage_out[slot ^ 1] + (size_t)recurse_on * d;
+        const int64_t ld_in = l == 0 ? d : 2 * (int64_t)d;
+        float* out = g->d_stage_out[slot];
+        // level l-2 used this slot: its device->host copy must have drained
+        if (l >= 2) GR_CUDA_TRY(cudaStreamWaitEvent(st, g->ev_copied[slot], 0));
+        if (int rc = gr_refex_aggregate_f32(g, in, ld_in, d, 0, g->n_rows, out, out + d,
+                                            2 * (int64_t)d, st))
+            return rc;
+        GR_CUDA_TRY(cudaEventRecord(g->ev_level[slot], st));
+        GR_CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->ev_level[slot], 0));
+        GR_CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)l * out_floats, out,
+                                    out_floats * sizeof(float), cudaMemcpyDeviceToHost,
+                                    g->copy_stream));
+        GR_CUDA_TRY(cudaEventRecord(g->ev_copied[slot], g->copy_stream));
+    }
+    GR_CUDA_TRY(cudaStreamSynchronize(g->copy_stream));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    return GR_OK;
+}

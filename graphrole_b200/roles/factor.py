@@ -1,0 +1,173 @@
+"""Hot path B: the RolX non-negative matrix factorisation, on the GPU.
+
+`get_nmf_decomposition(X, n_roles)` has the contract of graphrole/roles/factor.py:10-26, which
+wraps sklearn NMF(solver='mu', init='nndsvda') (sklearn/decomposition/_nmf.py:726-888).  Here
+the multiplicative-update loop is the CUDA library's gr_nmf_mu_f32 (include/graphrole_b200.h);
+the NNDSVDa start is computed on the device with torch.linalg (not a hot path, SURVEY.md
+section 8 row B2).
+"""
+import warnings
+from ctypes import byref, c_double, c_int32, c_void_p
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from graphrole_b200 import _native
+from graphrole_b200.types import FactorTuple
+
+# sklearn NMF defaults the reference relies on (_nmf.py:1533-1548)
+MAX_ITER = 200
+TOL = 1e-4
+CHECK_EVERY = 10
+
+
+def get_nmf_decomposition(X: np.ndarray, n_roles: int) -> FactorTuple:
+    """
+    Compute NMF decomposition X ~= G F
+    :param X: matrix to factor (n_nodes x n_features, non-negative)
+    :param n_roles: rank of decomposition
+    :return: (G [n_nodes, n_roles], F [n_roles, n_features]) as float64 ndarrays
+    """
+    X = np.asarray(X)
+    if X.ndim != 2:
+        raise ValueError('X must be a 2-D array')
+    if np.any(X < 0):
+        raise ValueError('Negative values in data passed to NMF')
+    device = torch.device('cuda', torch.cuda.current_device())
+    Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32), device=device)
+    W0, H0 = nndsvda_init(Xd, n_roles)
+    W, H, _, _ = nmf_mu(Xd, W0, H0, max_iter=MAX_ITER, tol=TOL)
+    return W.double().cpu().numpy(), H.double().cpu().numpy()
+
+
+def nmf_mu(X: torch.Tensor, W0: torch.Tensor, H0: torch.Tensor, max_iter: int = MAX_ITER,
+           tol: float = TOL, check_every: int = CHECK_EVERY, use_tf32: bool = True,
+           stream=None) -> Tuple[torch.Tensor, torch.Tensor, int, float]:
+    """Multiplicative-update NMF from an explicit start (sklearn's init='custom').
+
+    X [n, f], W0 [n, r], H0 [r, f]: float32 CUDA tensors.  Returns (W, H, n_iter, error) with
+    error = ||X - W H||_F at the last convergence check.
+    """
+    for name, t in (('X', X), ('W0', W0), ('H0', H0)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+            raise ValueError(f'{name} must be a 2-D float32 CUDA tensor')
+    n, f = X.shape
+    r = W0.shape[1]
+    if W0.shape != (n, r) or H0.shape != (r, f):
+        raise ValueError('shapes must be X [n, f], W0 [n, r], H0 [r, f]')
+    if X.stride(1) != 1:
+        X = X.contiguous()
+    lib = _native.load()
+    W = W0.clone().contiguous()
+    H = H0.clone().contiguous()
+    handle = c_void_p()
+    with torch.cuda.device(X.device):
+        _native.check(lib.gr_nmf_create(byref(handle), n, f, r, X.device.index or 0),
+                      'gr_nmf_create')
+        try:
+            n_iter, err = c_int32(0), c_double(0.0)
+            _native.check(lib.gr_nmf_mu_f32(
+                handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
+                c_void_p(H.data_ptr()), max_iter, float(tol), check_every,
+                1 if use_tf32 else 0, byref(n_iter), byref(err), _native._stream_ptr(stream)),
+                'gr_nmf_mu_f32')
+        finally:
+            lib.gr_nmf_destroy(handle)
+    return W, H, int(n_iter.value), float(err.value)
+
+
+def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor) -> float:
+    """||X - W H||_F evaluated by the library (dense residual, fp64 accumulation)."""
+    n, f = X.shape
+    r = W.shape[1]
+    lib = _native.load()
+    handle = c_void_p()
+    W = W.contiguous()
+    H = H.contiguous()
+    with torch.cuda.device(X.device):
+        _native.check(lib.gr_nmf_create(byref(handle), n, f, r, X.device.index or 0),
+                      'gr_nmf_create')
+        try:
+            err = c_double(0.0)
+            _native.check(lib.gr_nmf_error_f32(
+                handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
+                c_void_p(H.data_ptr()), byref(err), _native._stream_ptr(None)),
+                'gr_nmf_error_f32')
+        finally:
+            lib.gr_nmf_destroy(handle)
+    return float(err.value)
+
+
+def nndsvda_init(X: torch.Tensor, n_components: int, eps: float = 1e-6,
+                 n_oversamples: int = 10,
+                 seed: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """NNDSVDa start (Boutsidis & Gallopoulos 2008; sklearn _nmf.py:214-366) on the device.
+
+    The truncated SVD is a randomised subspace iteration (Halko et al. 2011) like sklearn's
+    `_randomized_svd`; its Gaussian test matrix is drawn from NumPy's global RNG (or `seed`),
+    so `np.random.seed` makes the start reproducible exactly as it does for the reference.
+    """
+    n, f = X.shape
+    if n_components > min(n, f):
+        raise ValueError("init = 'nndsvda' can only be used when "
+                         'n_components <= min(n_samples, n_features)')
+    rng = np.random.mtrand._rand if seed is None else np.random.RandomState(seed)
+    k = min(n_components + n_oversamples, min(n, f))
+    n_iter = 7 if n_components < 0.1 * min(n, f) else 4
+    work = torch.float64 if n * f <= (1 << 26) else torch.float32
+    A = X.to(work)
+    Q = torch.from_numpy(rng.normal(size=(f, k))).to(X.device, work)
+    Q, _ = torch.linalg.qr(A @ Q)
+    for _ in range(n_iter):
+        Q, _ = torch.linalg.qr(A.T @ Q)
+        Q, _ = torch.linalg.qr(A @ Q)
+    B = Q.T @ A                                   # k x f
+    Ub, S, Vt = torch.linalg.svd(B.double(), full_matrices=False)
+    U = (Q.double() @ Ub)[:, :n_components]
+    S = S[:n_components]
+    Vt = Vt[:n_components]
+    # sign convention: largest-magnitude entry of every left vector is positive
+    idx = U.abs().argmax(dim=0)
+    signs = torch.sign(U[idx, torch.arange(n_components, device=U.device)])
+    signs[signs == 0] = 1
+    U = U * signs
+    Vt = Vt * signs[:, None]
+
+    W = torch.zeros_like(U)
+    H = torch.zeros_like(Vt)
+    W[:, 0] = S[0].sqrt() * U[:, 0].abs()
+    H[0] = S[0].sqrt() * Vt[0].abs()
+    for j in range(1, n_components):
+        x, y = U[:, j], Vt[j]
+        xp, yp = x.clamp(min=0), y.clamp(min=0)
+        xn, yn = (-x).clamp(min=0), (-y).clamp(min=0)
+        mp = xp.norm() * yp.norm()
+        mn = xn.norm() * yn.norm()
+        if mp > mn:
+            u, v, sigma = xp / xp.norm(), yp / yp.norm(), mp
+        else:
+            u, v, sigma = xn / xn.norm(), yn / yn.norm(), mn
+        scale = (S[j] * sigma).sqrt()
+        W[:, j] = scale * u
+        H[j] = scale * v
+    W[W < eps] = 0
+    H[H < eps] = 0
+    avg = X.double().mean()
+    W[W == 0] = avg
+    H[H == 0] = avg
+    return W.float().contiguous(), H.float().contiguous()
+
+
+def encode(X: np.ndarray, n_bins: int) -> np.ndarray:
+    """Quantise X to n_bins levels with a Lloyd-Max quantiser (1-D k-means on the entries),
+    as graphrole/roles/factor.py:29-49 does; raises ValueError when n_bins exceeds the
+    number of entries (callers rely on that)."""
+    from sklearn.cluster import KMeans
+    flat = np.asarray(X, dtype=np.float64).reshape(-1, 1)
+    quantizer = KMeans(n_clusters=n_bins, random_state=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        quantizer.fit(flat)
+    levels = quantizer.cluster_centers_.ravel()
+    return levels[quantizer.labels_].reshape(np.shape(X))

@@ -1,0 +1,132 @@
+/*
+ * graphrole_b200.h — C-ABI of libgraphrole_b200.so (sm_100a).
+ *
+ * The reference (dkaslovsky/GraphRole) is pure Python and has no FFI of its own; its two
+ * data-parallel hot paths are Python-level call sites.  This header is the boundary a
+ * maintainer of the reference would bind with ctypes to replace
+ *
+ *   path A  RecursiveFeatureExtractor._get_next_features
+ *           graphrole/features/extract.py:98-119  (+ naming/layout step :144-163)
+ *   path B  get_nmf_decomposition
+ *           graphrole/roles/factor.py:10-26  ->  sklearn/decomposition/_nmf.py:726-888
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every entry point returns an int status
+ *     (GR_OK == 0).  gr_last_error() returns a thread-local, NUL-terminated description of the
+ *     most recent failure on the calling thread.
+ *   - pointers named *_dev are device pointers owned by the caller (e.g. torch
+ *     Tensor.data_ptr()); pointers named *_host are host pointers owned by the caller.  The
+ *     library owns only the opaque handles it returns and the workspaces inside them.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-buffer
+ *     entry points are asynchronous with respect to the host; *_host entry points synchronise
+ *     the stream before returning.
+ *   - one host thread per handle at a time; distinct handles may be used concurrently.
+ */
+#ifndef GRAPHROLE_B200_H
+#define GRAPHROLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    GR_OK = 0,
+    GR_ERR_INVALID_ARGUMENT = 1,   /* bad shape / alignment / null pointer                   */
+    GR_ERR_INVALID_GRAPH = 2,      /* rowptr not monotone, colidx out of range, ...           */
+    GR_ERR_CUDA = 3,               /* a CUDA runtime call or kernel launch failed              */
+    GR_ERR_UNSUPPORTED_DEVICE = 4, /* not an sm_100 device: there is no fallback path          */
+    GR_ERR_OUT_OF_MEMORY = 5
+};
+
+/* ---- library ------------------------------------------------------------------------- */
+
+const char* gr_last_error(void);
+/* "graphrole_b200 <version> sm_100a" */
+const char* gr_version(void);
+/* Number of kernels this library has launched on the calling process since load
+ * (monotone counter; bench.py differences it around the timed region). */
+int64_t gr_kernel_launch_count(void);
+
+/* ---- graph handle: the CSR form of graph.get_nodes()/get_neighbors() -------------------
+ * Replaces the per-node neighbour lookups of
+ *   graphrole/graph/interface/base.py:58-69, interface/networkx.py:36-46.
+ * Row i of the CSR is the i-th node label in sorted order (base.py:24-25, extract.py:129);
+ * colidx holds each row's UNIQUE out-neighbours (edge weights are ignored on this path,
+ * a self loop contributes the node once).  Duplicate column indices inside a row are
+ * accepted and counted as separate arcs.
+ *
+ * n_rows  rows held by this handle (a node-range shard holds a slice of the rows)
+ * n_cols  number of rows of the feature matrices that colidx may address (global node count)
+ * rowptr  int64[n_rows + 1], rowptr[0] == 0, rowptr[n_rows] == nnz, non-decreasing
+ * colidx  int32[nnz], values in [0, n_cols)
+ * The arrays are NOT copied: they must stay valid and unchanged until gr_csr_destroy().
+ * validate != 0 also range-checks colidx on the device (one extra pass over colidx).
+ */
+typedef struct gr_csr gr_csr_t;
+
+int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                  const int64_t* rowptr_dev, const int32_t* colidx_dev,
+                  int device, int validate);
+int gr_csr_destroy(gr_csr_t* g);
+/* n_rows, n_cols, nnz, number of hub rows (rows split across warps), number of hub segments */
+int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                int64_t* n_hub_rows, int64_t* n_hub_segments);
+
+/* ---- path A: one ReFeX recursion level -------------------------------------------------
+ * Replaces graphrole/features/extract.py:105-118 (reindex -> agg([sum, mean]) -> fillna(0))
+ * for all rows r in [row_lo, row_hi) of the handle:
+ *     out_sum [r * ldo + c] = sum_{k in rowptr[r]..rowptr[r+1]} X[colidx[k] * ldx + c]
+ *     out_mean[r * ldo + c] = out_sum / deg(r)            (0 when deg(r) == 0, extract.py:113)
+ * for c in [0, d).  Column order of the pair (out_sum, out_mean) is the reference's
+ * agg-major order (extract.py:158-162): pass out_mean = out_sum + d with ldo = 2*d to get the
+ * reference's [c1(sum)..cd(sum), c1(mean)..cd(mean)] row layout in one buffer.
+ * Either output pointer may be NULL to skip that aggregation.
+ * fp32 storage; per-lane multi-accumulator fp32 sums, hub rows combined in fp64.
+ * X must not alias the outputs.
+ */
+int gr_refex_aggregate_f32(gr_csr_t* g, const float* X_dev, int64_t ldx, int32_t d,
+                           int64_t row_lo, int64_t row_hi,
+                           float* out_sum_dev, float* out_mean_dev, int64_t ldo,
+                           void* stream);
+
+/* Host-buffer variant (the call a ctypes binding inside the reference would make with
+ * DataFrame.values): copies X (n_cols x d, row stride ldx) to the device, runs `levels`
+ * recursion levels and copies every level's [n_rows, 2*d] (sum block | mean block) result
+ * back.  Level l+1 aggregates the `recurse_on` block of level l (0 = sum, 1 = mean).
+ * out_host: levels * n_rows * 2*d floats, level-major.  Synchronous. */
+int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,
+                             int32_t levels, int32_t recurse_on, float* out_host, void* stream);
+
+/* ---- path B: RolX NMF, multiplicative updates, Frobenius loss ---------------------------
+ * Replaces sklearn.decomposition._nmf._fit_multiplicative_update (beta_loss=2, no
+ * regularisation; _nmf.py:726-888) as called from graphrole/roles/factor.py:19-25.
+ *   X  [n, f] row stride ldx, non-negative           W [n, r] row stride r (in: W0, out: W)
+ *   H  [r, f] row stride f (in: H0, out: H)
+ * Each iteration:  W *= (X H^T) / (W (H H^T));  H *= (W^T X) / ((W^T W) H)  with zero
+ * denominators replaced by float32 eps (_nmf.py:32,615,701).  Every `check_every`
+ * iterations (sklearn: 10) the Frobenius error ||X - W H||_F is evaluated and the loop stops
+ * when (previous_error - error) / error_at_init < tol (_nmf.py:867-879).  tol == 0 disables
+ * the test.  n_iter_out receives the number of iterations done, err_out the last evaluated
+ * error (error at init when never evaluated).
+ * Contractions run on tcgen05 tensor cores in TF32 with fp32 accumulation (use_tf32 != 0)
+ * or on fp32 FFMA (use_tf32 == 0).  Asynchronous inputs, but the call synchronises the stream
+ * at every convergence check (the stopping rule is data dependent).
+ */
+typedef struct gr_nmf gr_nmf_t;
+
+int gr_nmf_create(gr_nmf_t** out, int64_t n, int32_t f, int32_t r, int device);
+int gr_nmf_destroy(gr_nmf_t* h);
+int gr_nmf_mu_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
+                  float* W_dev, float* H_dev,
+                  int32_t max_iter, double tol, int32_t check_every, int32_t use_tf32,
+                  int32_t* n_iter_out, double* err_out, void* stream);
+/* Frobenius error ||X - W H||_F (dense-residual form, _nmf.py:122), fp64 accumulation. */
+int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
+                     const float* W_dev, const float* H_dev, double* err_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHROLE_B200_H */

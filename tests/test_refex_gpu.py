@@ -1,0 +1,250 @@
+"""Parity of hot path A on the GPU (through the C-ABI) against the pinned oracle and the
+reference's golden vectors.
+
+Tolerance (north_star): feature matrices within 1e-5 relative in fp32.  Stated here as
+|gpu - ref| <= 1e-5 * (|ref| + sum_k |x_k| * 2^-20)  -- i.e. 1e-5 relative to the value, with
+the forward-error scale of the row's absolute sum covering cancellation for signed inputs.
+Integer-valued inputs (the reference's level-0 features) must come back exact.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from graphrole_b200 import RecursiveFeatureExtractor, _native
+from graphrole_b200.graph.csr import CSRGraph
+from oracle import refex_oracle as oracle
+from helpers import (PATH4_EXPECTED, RANDOM_CASES, frame_from_json, graph_from_json,
+                     random_case)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def gpu_aggregate(g, X, **kw):
+    h = g.handle('cuda:0')
+    out = h.aggregate(torch.as_tensor(X, dtype=torch.float32, device='cuda:0'), **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def assert_parity(got, rp, ci, X32):
+    S, M = oracle.aggregate_csr(rp, ci, X32.astype(np.float64))
+    Sabs, Mabs = oracle.aggregate_csr(rp, ci, np.abs(X32).astype(np.float64))
+    d = X32.shape[1]
+    for part, ref, scale in ((got[:, :d], S, Sabs), (got[:, d:], M, Mabs)):
+        err = np.abs(part.astype(np.float64) - ref)
+        bound = RTOL * (np.abs(ref) + scale * 2.0 ** -20) + 1e-30
+        assert (err <= bound).all(), f'max rel err {np.max(err / (np.abs(ref) + 1e-30)):.3e}'
+
+
+def test_native_library_is_loaded():
+    lib = _native.load()
+    assert b'sm_100a' in lib.gr_version()
+    before = _native.launch_count()
+    g = CSRGraph.from_edges([0, 1], [1, 2], n=3)
+    gpu_aggregate(g, np.ones((3, 4), dtype=np.float32))
+    assert _native.launch_count() > before
+
+
+@pytest.mark.parametrize('name', RANDOM_CASES)
+def test_random_graphs_vs_reference_golden(refex_random, name):
+    directed, n, src, dst, X, out_index, out_cols, out = random_case(refex_random, name)
+    g = CSRGraph.from_edges(src, dst, n=n, directed=directed)
+    got = gpu_aggregate(g, X.astype(np.float32))
+    rp, ci = g.host_arrays()
+    assert_parity(got, rp, ci, X.astype(np.float32))
+    # and directly against what the reference printed (float64 inputs -> allow input rounding)
+    np.testing.assert_allclose(got[out_index], out, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('d', [1, 2, 3, 4, 5, 8, 12, 16, 31, 32, 33, 64, 100, 128, 130, 256, 260])
+def test_feature_widths(d):
+    rng = np.random.RandomState(d)
+    n = 500
+    src = rng.randint(0, n, 4000)
+    dst = rng.randint(0, n, 4000)
+    g = CSRGraph.from_edges(src, dst, n=n, directed=True)
+    X = rng.rand(n, d).astype(np.float32)
+    got = gpu_aggregate(g, X)
+    rp, ci = g.host_arrays()
+    assert_parity(got, rp, ci, X)
+
+
+def test_strided_input_and_row_ranges():
+    rng = np.random.RandomState(0)
+    n, d = 700, 24
+    g = CSRGraph.from_edges(rng.randint(0, n, 9000), rng.randint(0, n, 9000), n=n)
+    wide = torch.as_tensor(rng.rand(n, 64).astype(np.float32), device='cuda:0')
+    rp, ci = g.host_arrays()
+    for c0 in (0, 4, 5):       # 5: misaligned -> scalar path
+        X = wide[:, c0:c0 + d]
+        full = g.handle('cuda:0').aggregate(X).cpu().numpy()
+        assert_parity(full, rp, ci, X.cpu().numpy())
+        for lo, hi in ((0, 1), (13, 14), (100, 555), (699, 700), (0, 700), (7, 7)):
+            part = g.handle('cuda:0').aggregate(X, row_lo=lo, row_hi=hi).cpu().numpy()
+            np.testing.assert_array_equal(part, full[lo:hi])
+
+
+def test_integer_features_are_exact_and_dangling_rows_zero():
+    rng = np.random.RandomState(1)
+    n = 300
+    src, dst = rng.randint(0, 200, 1500), rng.randint(0, 200, 1500)   # nodes >= 200 isolated
+    g = CSRGraph.from_edges(src, dst, n=n)
+    X = rng.randint(0, 50, size=(n, 3)).astype(np.float32)
+    got = gpu_aggregate(g, X)
+    rp, ci = g.host_arrays()
+    S, M = oracle.aggregate_csr(rp, ci, X)
+    np.testing.assert_array_equal(got[:, :3], S.astype(np.float32))
+    np.testing.assert_allclose(got[:, 3:], M, rtol=1e-6)
+    assert not got[200:].any()
+    assert not np.isnan(got).any()
+
+
+def test_hub_rows_are_split_and_deterministic():
+    """Power-law style: a few rows far above the hub threshold (2048 arcs)."""
+    rng = np.random.RandomState(2)
+    n, d = 30000, 64
+    hubs = np.array([0, 7, 29999])
+    src = np.concatenate([np.repeat(hubs, [20000, 5000, 2049]), rng.randint(0, n, 60000)])
+    dst = np.concatenate([rng.choice(n, 20000, replace=False), rng.choice(n, 5000, replace=False),
+                          rng.choice(n, 2049, replace=False), rng.randint(0, n, 60000)])
+    g = CSRGraph.from_edges(src, dst, n=n, directed=True)
+    info = g.handle('cuda:0').info()
+    assert info['n_hub_rows'] == 3 and info['n_hub_segments'] == 20 + 5 + 3
+    X = (rng.rand(n, d) * 2 - 0.5).astype(np.float32)
+    got = gpu_aggregate(g, X)
+    rp, ci = g.host_arrays()
+    assert_parity(got, rp, ci, X)
+    again = gpu_aggregate(g, X)
+    np.testing.assert_array_equal(got, again)        # bitwise reproducible
+    # hub rows inside / outside a row range
+    part = g.handle('cuda:0').aggregate(torch.as_tensor(X, device='cuda:0'), row_lo=5,
+                                        row_hi=n).cpu().numpy()
+    np.testing.assert_array_equal(part, got[5:])
+
+
+def test_empty_graph_rows_and_invalid_inputs():
+    g = CSRGraph(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    got = gpu_aggregate(g, np.ones((5, 4), dtype=np.float32))
+    assert got.shape == (5, 8) and not got.any()
+    bad = CSRGraph(np.array([0, 2, 1]), np.array([0, 1], dtype=np.int32))
+    with pytest.raises(ValueError):
+        bad.handle('cuda:0')
+    bad = CSRGraph(np.array([0, 1, 2]), np.array([0, 5], dtype=np.int32))
+    with pytest.raises(ValueError):
+        bad.handle('cuda:0')
+    good = CSRGraph.from_edges([0], [1], n=2)
+    with pytest.raises(ValueError):
+        good.handle('cuda:0').aggregate(torch.ones(3, 4, device='cuda:0'))
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    rng = np.random.RandomState(3)
+    n, d, levels = 4000, 32, 3
+    g = CSRGraph.from_edges(rng.randint(0, n, 40000), rng.randint(0, n, 40000), n=n)
+    X = torch.from_numpy(rng.rand(n, d).astype(np.float32)).pin_memory()
+    h = g.handle('cuda:0')
+    out = h.levels_host(X, levels, recurse_on='mean').numpy()
+    cur = X.cuda()
+    for l in range(levels):
+        lvl = h.aggregate(cur)
+        np.testing.assert_array_equal(out[l], lvl.cpu().numpy())
+        cur = lvl[:, d:]
+    rp, ci = g.host_arrays()
+    assert_parity(out[0], rp, ci, X.numpy())
+
+
+# ---- the reference's API surface on top of the kernel -----------------------------------
+
+def seeded(G, **kw):
+    rfe = RecursiveFeatureExtractor(G, aggs=[np.sum, np.mean], **kw)
+    rfe._features = rfe.graph.get_neighborhood_features()
+    rfe._final_features = {0: rfe._features.to_dict()}
+    rfe.generation_count = 1
+    return rfe
+
+
+def test_get_next_features_known_answer(refex_cases):
+    """Reference KAT, tests/test_features/test_extract.py:104-122, through the GPU."""
+    G = graph_from_json(refex_cases['path4']['graph'])
+    got = seeded(G)._get_next_features()
+    expected = pd.DataFrame(PATH4_EXPECTED)
+    assert np.allclose(got.sort_index(axis=1).sort_index(axis=0).values,
+                       expected.sort_index(axis=1).sort_index(axis=0).values)
+    ref = frame_from_json(refex_cases['path4']['next'])
+    assert list(got.columns) == list(ref.columns) and list(got.index) == list(ref.index)
+
+
+@pytest.mark.parametrize('name', ['dangling', 'directed_weighted', 'undirected_weighted',
+                                  'attributes'])
+def test_get_next_features_small_cases(refex_cases, name):
+    case = refex_cases[name]
+    G = graph_from_json(case['graph'], case.get('node_attrs'))
+    kw = {'attributes': True} if name == 'attributes' else {}
+    got = seeded(G, **kw)._get_next_features()
+    ref = frame_from_json(case['next'])
+    assert list(got.columns) == list(ref.columns)
+    assert list(got.index) == list(ref.index)
+    np.testing.assert_allclose(got.values, ref.values, rtol=RTOL, atol=1e-12)
+    assert got.notnull().all().all()
+
+
+@pytest.mark.parametrize('name', ['dangling', 'directed_weighted', 'undirected_weighted',
+                                  'karate', 'karate_weighted'])
+def test_extract_features_end_to_end(refex_cases, name):
+    case = refex_cases[name]
+    G = graph_from_json(case['graph'])
+    rfe = RecursiveFeatureExtractor(G)          # default aggs work here (pandas-3 safe)
+    got = rfe.extract_features()
+    ref = frame_from_json(case['features'])
+    assert rfe.generation_count == case['generation_count']
+    assert list(got.columns) == list(ref.columns)
+    assert list(got.index) == list(ref.index)
+    np.testing.assert_allclose(got.values.astype(float), ref.values, rtol=RTOL, atol=1e-12)
+    if name == 'karate':
+        assert {str(k): sorted(v) for k, v in rfe._final_features.items()} == \
+            case['retained_by_generation']
+        nb = case['notebook_table']
+        np.testing.assert_allclose(got[nb['columns']].values, np.array(nb['values']),
+                                   atol=5.1e-7 + 1e-5)
+    # memoised second call (tests/test_features/test_extract.py:210-214)
+    pd.testing.assert_frame_equal(got, rfe.extract_features())
+
+
+def test_missing_rows_are_skipped_like_pandas_skipna():
+    G = graph_from_json({'directed': False, 'nodes': [0, 1, 2, 3], 'weighted': False,
+                         'edges': [[0, 1, 1], [0, 2, 1], [2, 3, 1]]})
+    rfe = seeded(G)
+    rfe._features = rfe._features.drop(index=[1])    # neighbour without a feature row
+    got = rfe._get_next_features()
+    feats = rfe._features
+    exp = oracle.pandas_chain_rows(feats.reindex(range(4)), feats.columns, range(4),
+                                   *rfe.graph.to_csr().host_arrays())
+    np.testing.assert_allclose(got.values, exp.values, rtol=RTOL)
+
+
+@pytest.mark.parametrize('n,deg,d', [(200_000, 16, 32), (100_000, 40, 64)])
+def test_larger_random_graph_properties(n, deg, d):
+    """Sizes the oracle still finishes in seconds, plus size-independent properties:
+    linearity, mean*deg == sum, and column sums (a checksum of checksums)."""
+    from graphrole_b200.graph.generators import erdos_renyi_csr
+    g = erdos_renyi_csr(n, n * deg // 2, seed=5, device='cuda:0')
+    h = g.handle('cuda:0')
+    gen = torch.Generator(device='cuda:0').manual_seed(1)
+    X = torch.rand(n, d, device='cuda:0', generator=gen)
+    Y = torch.rand(n, d, device='cuda:0', generator=gen)
+    ox, oy, oxy = h.aggregate(X), h.aggregate(Y), h.aggregate(X + 2 * Y)
+    torch.testing.assert_close(oxy, ox + 2 * oy, rtol=1e-5, atol=1e-5)
+    degs = g.out_degree().to(torch.float32)[:, None]
+    torch.testing.assert_close(ox[:, d:] * degs, ox[:, :d], rtol=1e-5, atol=1e-6)
+    # sum over rows of S = sum over nodes of indegree * x (undirected: = outdegree)
+    lhs = ox[:, :d].double().sum(0)
+    rhs = (X.double() * degs.double()).sum(0)
+    torch.testing.assert_close(lhs, rhs, rtol=1e-6, atol=0)
+    rp, ci = g.host_arrays()
+    rows = np.random.RandomState(0).choice(n, 3000, replace=False)
+    S, M = oracle.aggregate_rows_c(rows, rp, ci, X.cpu().numpy())
+    got = ox.cpu().numpy()[rows]
+    np.testing.assert_allclose(got[:, :d], S, rtol=RTOL)
+    np.testing.assert_allclose(got[:, d:], M, rtol=RTOL)

@@ -1,0 +1,91 @@
+"""Host-side logic of the node-range sharded recursion, exercised with world_size-2 gloo
+processes on CPU.  The per-shard aggregation is done by the oracle here (tests may use it);
+what is under test is the range computation, the shard slicing and the in-place exchange."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from graphrole_b200.graph.generators import barabasi_albert_csr, erdos_renyi_csr
+from graphrole_b200.shard import exchange_rows, nnz_balanced_ranges
+from oracle import refex_oracle as oracle
+
+
+def test_ranges_cover_all_rows_and_balance_arcs():
+    g = barabasi_albert_csr(50_000, 10, seed=1, device='cpu')
+    for world in (1, 2, 3, 4, 8):
+        ranges = nnz_balanced_ranges(g.rowptr, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == g.n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        arcs = [int(g.rowptr[hi] - g.rowptr[lo]) for lo, hi in ranges]
+        assert sum(arcs) == g.nnz
+        assert max(arcs) - min(arcs) <= 2 * int(g.out_degree().max())
+
+
+def test_ranges_degenerate():
+    rowptr = torch.zeros(5, dtype=torch.int64)
+    assert nnz_balanced_ranges(rowptr, 3)[-1][1] == 4
+    rowptr = torch.tensor([0, 10, 10, 10])
+    ranges = nnz_balanced_ranges(rowptr, 4)
+    assert sum(hi - lo for lo, hi in ranges) == 3
+
+
+def test_row_slice_keeps_global_columns():
+    g = erdos_renyi_csr(2000, 10000, seed=2, device='cpu')
+    s = g.row_slice(500, 1200)
+    assert s.n == 700 and s.n_cols == 2000 and int(s.rowptr[0]) == 0
+    rp, ci = g.host_arrays()
+    np.testing.assert_array_equal(s.colidx.numpy(), ci[rp[500]:rp[1200]])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, levels, equal_rows, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = barabasi_albert_csr(3000, 6, seed=3, device='cpu')
+        d = 5
+        X0 = torch.rand(g.n, d, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+        if equal_rows:
+            ranges = [(k * g.n // world, (k + 1) * g.n // world) for k in range(world)]
+        else:
+            ranges = nnz_balanced_ranges(g.rowptr, world)
+        lo, hi = ranges[rank]
+        shard = g.row_slice(lo, hi)
+        rp, ci = shard.host_arrays()
+        cur = X0
+        for _ in range(levels):
+            nxt = torch.full((g.n, d), float('nan'), dtype=torch.float64)
+            _, M = oracle.aggregate_csr(rp, ci, cur.numpy())
+            nxt[lo:hi] = torch.from_numpy(M)
+            exchange_rows(nxt, ranges, rank, dist)
+            cur = nxt
+        ret[rank] = cur.numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('equal_rows', [False, True])
+def test_two_rank_recursion_equals_single_process(equal_rows):
+    world, levels = 2, 3
+    port = _free_port()
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_worker, args=(world, port, levels, equal_rows, ret), nprocs=world, join=True)
+    g = barabasi_albert_csr(3000, 6, seed=3, device='cpu')
+    rp, ci = g.host_arrays()
+    cur = torch.rand(g.n, 5, generator=torch.Generator().manual_seed(0),
+                     dtype=torch.float64).numpy()
+    for _ in range(levels):
+        _, cur = oracle.aggregate_csr(rp, ci, cur)
+    for rank in range(world):
+        np.testing.assert_allclose(ret[rank], cur, rtol=1e-13, atol=0)
