@@ -17,6 +17,8 @@ GR_ERR_INVALID_GRAPH = 2
 GR_ERR_CUDA = 3
 GR_ERR_UNSUPPORTED_DEVICE = 4
 GR_ERR_OUT_OF_MEMORY = 5
+GR_CSR_VALIDATE = 1
+GR_CSR_HOT_HINTS = 2
 
 # every symbol include/graphrole_b200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -27,7 +29,7 @@ SIGNATURES = {
                               c_int, c_int]),
     'gr_csr_destroy': (c_int, [c_void_p]),
     'gr_csr_info': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
-                            POINTER(c_int64), POINTER(c_int64)]),
+                            POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     'gr_refex_aggregate_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
                                        c_void_p, c_void_p, c_int64, c_void_p]),
     'gr_refex_levels_host_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
@@ -108,7 +110,7 @@ def _stream_ptr(stream):
 class CsrHandle:
     """Owner of a gr_csr_t*.  Keeps the rowptr/colidx tensors alive (the library does not copy)."""
 
-    def __init__(self, rowptr, colidx, n_cols=None, validate=True):
+    def __init__(self, rowptr, colidx, n_cols=None, validate=True, hot_hints=True):
         import torch
         lib = load()
         if not (rowptr.is_cuda and colidx.is_cuda):
@@ -128,14 +130,16 @@ class CsrHandle:
         check(lib.gr_csr_create(byref(handle), self.n_rows, self.n_cols, self.nnz,
                                 c_void_p(self.rowptr.data_ptr()),
                                 c_void_p(self.colidx.data_ptr()),
-                                self.device.index or 0, 1 if validate else 0),
+                                self.device.index or 0,
+                                (GR_CSR_VALIDATE if validate else 0)
+                                | (GR_CSR_HOT_HINTS if hot_hints else 0)),
               'gr_csr_create')
         self._handle = handle
 
     def info(self):
-        vals = [c_int64() for _ in range(5)]
+        vals = [c_int64() for _ in range(6)]
         check(load().gr_csr_info(self._handle, *[byref(v) for v in vals]), 'gr_csr_info')
-        keys = ('n_rows', 'n_cols', 'nnz', 'n_hub_rows', 'n_hub_segments')
+        keys = ('n_rows', 'n_cols', 'nnz', 'n_hub_rows', 'n_hub_segments', 'n_hot_rows')
         return {k: int(v.value) for k, v in zip(keys, vals)}
 
     def aggregate(self, X, out=None, row_lo=0, row_hi=None, stream=None):

@@ -35,6 +35,92 @@ colidx_range_kernel(const int32_t* __restrict__ colidx, int64_t nnz, int64_t n_c
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(bad, local);
 }
 
+// ---- GR_CSR_HOT_HINTS: in-degree -> threshold -> sign-bit tagged copy of colidx -------------
+__global__ void __launch_bounds__(256)
+indegree_kernel(const int32_t* __restrict__ colidx, int64_t nnz, int64_t n_cols,
+                int32_t* __restrict__ indeg) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t c = __ldcs(colidx + i);
+        if (c >= 0 && (int64_t)c < n_cols) atomicAdd(indeg + c, 1);   // unvalidated input stays safe
+    }
+}
+
+constexpr int kDegBins = 1 << 16;
+
+__global__ void __launch_bounds__(256)
+degree_histogram_kernel(const int32_t* __restrict__ indeg, int64_t n,
+                        unsigned long long* __restrict__ hist) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(hist + min(indeg[i], kDegBins - 1), 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+tag_hot_kernel(const int32_t* __restrict__ colidx, int64_t nnz, int64_t n_cols,
+               const int32_t* __restrict__ indeg, int32_t threshold,
+               int32_t* __restrict__ tagged) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t c = __ldcs(colidx + i);
+        const bool hot = c >= 0 && (int64_t)c < n_cols && __ldg(indeg + c) >= threshold;
+        tagged[i] = hot ? (c | (int32_t)0x80000000) : c;
+    }
+}
+
+// Tags arcs into the (at most) kHotBudgetBytes / kHotRowBytes rows of highest in-degree.
+int build_hot_tags(gr_csr* g) {
+    if (g->nnz == 0 || g->n_cols == 0) return GR_OK;
+    const int64_t budget_rows = std::min<int64_t>(kHotBudgetBytes / kHotRowBytes, g->n_cols);
+    int32_t* indeg = nullptr;
+    unsigned long long* hist = nullptr;
+    std::vector<unsigned long long> h_hist(kDegBins);
+    const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(g->nnz, 256), 148 * 32);
+    int rc = GR_OK;
+    auto cleanup = [&]() { cudaFree(indeg); cudaFree(hist); };
+#define HOT_TRY(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            cleanup();                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? GR_ERR_OUT_OF_MEMORY : GR_ERR_CUDA, \
+                        "hot-row tagging: %s failed: %s", #expr, cudaGetErrorString(_e));   \
+        }                                                                                   \
+    } while (0)
+    HOT_TRY(cudaMalloc(&indeg, (size_t)g->n_cols * sizeof(int32_t)));
+    HOT_TRY(cudaMalloc(&hist, kDegBins * sizeof(unsigned long long)));
+    HOT_TRY(cudaMemset(indeg, 0, (size_t)g->n_cols * sizeof(int32_t)));
+    HOT_TRY(cudaMemset(hist, 0, kDegBins * sizeof(unsigned long long)));
+    indegree_kernel<<<blocks, 256>>>(g->colidx, g->nnz, g->n_cols, indeg);
+    degree_histogram_kernel<<<(int)std::min<int64_t>(ceil_div<int64_t>(g->n_cols, 256), 148 * 32),
+                              256>>>(indeg, g->n_cols, hist);
+    count_launch(2);
+    HOT_TRY(cudaGetLastError());
+    HOT_TRY(cudaMemcpy(h_hist.data(), hist, kDegBins * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost));
+    // smallest threshold whose row count fits the budget (threshold >= 2: a row gathered once
+    // has nothing to reuse)
+    int64_t rows_at_or_above = 0;
+    int32_t threshold = kDegBins;
+    for (int b = kDegBins - 1; b >= 2; --b) {
+        if (rows_at_or_above + (int64_t)h_hist[b] > budget_rows) break;
+        rows_at_or_above += (int64_t)h_hist[b];
+        threshold = b;
+    }
+    g->n_hot_rows = rows_at_or_above;
+    if (rows_at_or_above > 0) {
+        HOT_TRY(cudaMalloc(&g->d_colidx_tagged, (size_t)g->nnz * sizeof(int32_t)));
+        tag_hot_kernel<<<blocks, 256>>>(g->colidx, g->nnz, g->n_cols, indeg, threshold,
+                                         g->d_colidx_tagged);
+        count_launch();
+        HOT_TRY(cudaGetLastError());
+        HOT_TRY(cudaDeviceSynchronize());
+    }
+#undef HOT_TRY
+    cleanup();
+    return rc;
+}
+
 template <typename T>
 int upload(T** dst, const std::vector<T>& src) {
     *dst = nullptr;
@@ -48,7 +134,7 @@ int upload(T** dst, const std::vector<T>& src) {
 
 extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int64_t nnz,
                              const int64_t* rowptr_dev, const int32_t* colidx_dev,
-                             int device, int validate) {
+                             int device, int flags) {
     GR_REQUIRE(out != nullptr, "gr_csr_create: out is NULL");
     *out = nullptr;
     GR_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "gr_csr_create: negative size");
@@ -91,6 +177,11 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
             return fail(GR_ERR_INVALID_GRAPH, "rowptr decreases at row %lld (%lld -> %lld)",
                         (long long)r, (long long)b, (long long)e);
         }
+        if (e - rp[(size_t)std::max<int64_t>(r - 31, 0)] >= (int64_t)1 << 31) {
+            delete g;
+            return fail(GR_ERR_INVALID_GRAPH, "rows %lld..%lld hold more than 2^31 arcs",
+                        (long long)std::max<int64_t>(r - 31, 0), (long long)r);
+        }
         if (e - b > kHubThreshold) {
             g->h_hub_row.push_back(r);
             for (int64_t s = b; s < e; s += kHubSegment) {
@@ -111,7 +202,7 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
         return rc;
     }
 
-    if (validate && nnz > 0) {
+    if ((flags & GR_CSR_VALIDATE) && nnz > 0) {
         unsigned long long* d_bad = nullptr;
         unsigned long long h_bad = 0;
         cudaError_t e = cudaMalloc(&d_bad, sizeof(*d_bad));
@@ -136,6 +227,13 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
         }
     }
 
+    if (flags & GR_CSR_HOT_HINTS) {
+        if ((rc = build_hot_tags(g))) {
+            gr_csr_destroy(g);
+            return rc;
+        }
+    }
+
     *out = g;
     return GR_OK;
 }
@@ -148,6 +246,7 @@ extern "C" int gr_csr_destroy(gr_csr_t* g) {
     cudaFree(g->d_seg_begin);
     cudaFree(g->d_seg_end);
     cudaFree(g->d_partial);
+    cudaFree(g->d_colidx_tagged);
     cudaFree(g->d_stage_x);
     cudaFree(g->d_stage_out[0]);
     cudaFree(g->d_stage_out[1]);
@@ -161,12 +260,13 @@ extern "C" int gr_csr_destroy(gr_csr_t* g) {
 }
 
 extern "C" int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
-                           int64_t* n_hub_rows, int64_t* n_hub_segments) {
+                           int64_t* n_hub_rows, int64_t* n_hub_segments, int64_t* n_hot_rows) {
     GR_REQUIRE(g != nullptr, "gr_csr_info: handle is NULL");
     if (n_rows) *n_rows = g->n_rows;
     if (n_cols) *n_cols = g->n_cols;
     if (nnz) *nnz = g->nnz;
     if (n_hub_rows) *n_hub_rows = g->n_hub_rows;
     if (n_hub_segments) *n_hub_segments = g->n_segments;
+    if (n_hot_rows) *n_hot_rows = g->n_hot_rows;
     return GR_OK;
 }

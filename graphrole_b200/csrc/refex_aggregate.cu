@@ -9,11 +9,15 @@
 //   * a warp owns `rows_per_warp` CONSECUTIVE rows, so its colidx span is one contiguous
 //     stream, read in 128-byte-aligned chunks of 32 indices with one chunk of prefetch, and
 //     its rowptr entries are one coalesced load; only the X-row gathers are dependent loads;
-//   * a feature row (d floats) is covered by LPR = d/4 lanes with one float4 each; the
-//     32/LPR lane groups of the warp take different neighbours and every group keeps U
-//     independent loads (and U independent fp32 accumulators) in flight;
-//   * colidx and the outputs are touched once and use streaming (evict-first) accesses so L2
-//     is left to the gathered rows, which is where power-law graphs have reuse;
+//   * a feature row (d floats) is covered by LPR = d/4 lanes with one float4 each and the
+//     32/LPR lane groups of the warp take different neighbours.  Measured on B200
+//     (profiles/README.md): the kernel is bound by the number of warps with a gather in
+//     flight, not by loads per warp -- 32 registers / 64 resident warps per SM with ONE
+//     gather per lane beats every unrolled variant (23.8 -> 17.4 ms per level on C3);
+//   * colidx and the outputs are touched once and use streaming (evict-first) accesses, the
+//     gathers bypass L1 (no reuse there), and rows the handle tagged as hot (sign bit of the
+//     library's colidx copy, GR_CSR_HOT_HINTS) are loaded with an L2 evict_last policy so
+//     the rows power-law graphs keep coming back to stay resident in L2;
 //   * rows longer than kHubThreshold arcs are cut into kHubSegment-arc segments handled by
 //     the leading CTAs of the same launch; a small second kernel adds a row's partials in
 //     fp64 in segment order (bitwise reproducible, no float atomics).
@@ -26,7 +30,8 @@ using namespace gr;
 
 namespace {
 
-constexpr int kWarps = 8;  // 256 threads per CTA
+constexpr int kWarps = 8;      // 256 threads per CTA
+constexpr int kMinBlocks = 8;  // 32 registers/thread -> 64 resident warps per SM
 constexpr unsigned kFull = 0xffffffffu;
 
 struct RefexArgs {
@@ -48,18 +53,44 @@ struct RefexArgs {
 };
 
 // ---- vector helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// Gather of one lane's slice of a feature row: L1 bypassed (no reuse there); rows tagged hot
+// carry an L2 evict_last policy.  Cold rows use the plain form: measured on B200, attaching an
+// explicit evict_normal policy to every cold load costs 6 % (18.7 vs 17.6 ms per C3 level),
+// more than the occasional hot/cold divergence between lane groups.
 template <int VW>
-__device__ __forceinline__ void load_row(float (&v)[VW], const float* p, bool ok);
+__device__ __forceinline__ void load_row(float (&v)[VW], const float* p, bool ok, bool hot,
+                                         uint64_t policy);
 
 template <>
-__device__ __forceinline__ void load_row<4>(float (&v)[4], const float* p, bool ok) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+__device__ __forceinline__ void load_row<4>(float (&v)[4], const float* p, bool ok, bool hot,
+                                            uint64_t policy) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (ok) {
+        if (hot)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(policy));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    }
 }
 template <>
-__device__ __forceinline__ void load_row<1>(float (&v)[1], const float* p, bool ok) {
-    v[0] = ok ? __ldg(p) : 0.f;
+__device__ __forceinline__ void load_row<1>(float (&v)[1], const float* p, bool ok, bool hot,
+                                            uint64_t policy) {
+    v[0] = 0.f;
+    if (ok) {
+        if (hot)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;"
+                         : "=f"(v[0]) : "l"(p), "l"(policy));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
+    }
 }
 
 template <int VW>
@@ -76,22 +107,24 @@ __device__ __forceinline__ void store_stream<1>(float* p, const float (&v)[1], f
 }
 
 // ---- the warp's view of its contiguous colidx span --------------------------------------
+// Positions are 32-bit offsets from the 32-aligned arc position at or below the span start (a
+// span is at most 31 rows; gr_csr_create rejects graphs whose 32-row windows exceed 2^31 arcs).
 struct ArcStream {
-    const int32_t* __restrict__ colidx;
-    int64_t limit;  // positions >= limit are never dereferenced
-    int64_t base;   // 32-aligned position of the chunk held in `cur`
+    const int32_t* __restrict__ span;  // colidx + aligned span start
+    uint32_t limit;                    // span length: offsets >= limit are never dereferenced
+    uint32_t base;                     // offset of the chunk held in `cur` (multiple of 32)
     int32_t cur, nxt;
 
-    __device__ __forceinline__ int32_t fetch(int64_t p) const {
-        return p < limit ? __ldcs(colidx + p) : 0;
+    __device__ __forceinline__ int32_t fetch(uint32_t p) const {
+        return p < limit ? __ldcs(span + p) : 0;
     }
-    __device__ __forceinline__ void open(int64_t pos, int lane) {
-        base = pos & ~int64_t(31);
+    __device__ __forceinline__ void open(uint32_t pos, int lane) {
+        base = pos & ~31u;
         cur = fetch(base + lane);
         nxt = fetch(base + 32 + lane);
     }
     // make `pos` fall inside the current chunk (warp-uniform control flow)
-    __device__ __forceinline__ void seek(int64_t pos, int lane) {
+    __device__ __forceinline__ void seek(uint32_t pos, int lane) {
         if (pos < base + 32) return;
         if (pos < base + 64) {
             cur = nxt;
@@ -103,109 +136,105 @@ struct ArcStream {
     }
 };
 
-// Sum of X[colidx[k], col..col+VW) over k in [beg, end); result replicated in every lane group.
-template <int LPR, int VW, int U>
-__device__ __forceinline__ void reduce_arcs(ArcStream& s, int64_t beg, int64_t end,
+// Sum of X[colidx[k], col..col+VW) over span offsets k in [beg, end); result replicated in
+// every lane group.  One gather per lane in flight; 32/LPR lane groups -> that many
+// independent fp32 accumulators per column.
+template <int LPR, int VW>
+__device__ __forceinline__ void reduce_arcs(ArcStream& s, uint32_t beg, uint32_t end,
                                             const float* __restrict__ xcol, int64_t ldx,
-                                            bool col_ok, int lane, float (&total)[VW]) {
+                                            bool col_ok, int lane, uint64_t pol_hot,
+                                            float (&total)[VW]) {
     constexpr int G = 32 / LPR;
     const int grp = lane / LPR;
-    float acc[U][VW];
+    float acc[VW];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int c = 0; c < VW; ++c) acc[u][c] = 0.f;
+    for (int c = 0; c < VW; ++c) acc[c] = 0.f;
 
-    int64_t k = beg;
+    uint32_t k = beg;
     while (k < end) {
         s.seek(k, lane);
         const int off = (int)(k - s.base);
-        const int cnt = (int)min(end - k, (int64_t)(32 - off));
-        for (int t = 0; t < cnt; t += G * U) {
-            float v[U][VW];
+        const int cnt = (int)min(end - k, (uint32_t)(32 - off));
+#pragma unroll 4
+        for (int t = 0; t < cnt; t += G) {   // warp-uniform trip count (shuffles inside)
+            const int kk = t + grp;
+            const int32_t tagged = __shfl_sync(kFull, s.cur, (off + kk) & 31);
+            float v[VW];
+            load_row<VW>(v, xcol + (int64_t)(tagged & 0x7fffffff) * ldx, col_ok && kk < cnt,
+                         tagged < 0, pol_hot);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int kk = t + u * G + grp;
-                const int32_t idx = __shfl_sync(kFull, s.cur, (off + kk) & 31);
-                load_row<VW>(v[u], xcol + (int64_t)idx * ldx, col_ok && kk < cnt);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int c = 0; c < VW; ++c) acc[u][c] += v[u][c];
+            for (int c = 0; c < VW; ++c) acc[c] += v[c];
         }
         k += cnt;
     }
-    // pairwise combine of the U accumulators, then of the lane groups
-#pragma unroll
-    for (int step = 1; step < U; step <<= 1)
-#pragma unroll
-        for (int u = 0; u + step < U; u += 2 * step)
-#pragma unroll
-            for (int c = 0; c < VW; ++c) acc[u][c] += acc[u + step][c];
 #pragma unroll
     for (int c = 0; c < VW; ++c) {
-        float t = acc[0][c];
+        float t = acc[c];
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) t += __shfl_xor_sync(kFull, t, o);
         total[c] = t;
     }
 }
 
-template <int LPR, int VW, int U>
-__global__ void __launch_bounds__(kWarps * 32)
+// ---- the level kernel ----------------------------------------------------------------------
+// CTAs [0, n_seg_blocks): one warp per hub segment (kHubSegment arcs of a long row -> fp32
+// partial); they lead the grid so the long warps start first and overlap the ordinary rows.
+// Remaining CTAs: rows_per_warp consecutive ordinary rows per warp.
+template <int LPR, int VW>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 refex_gather_kernel(const RefexArgs a) {
     constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int sub = lane % LPR;
     const int grp = lane / LPR;
     const int col = ((int)blockIdx.y * LPR + sub) * VW;
     const bool col_ok = col < a.d;
     const float* xcol = a.X + col;
-
+    const uint64_t pol_hot = l2_policy_evict_last();
     ArcStream s;
-    s.colidx = a.colidx;
 
     if ((int64_t)blockIdx.x < a.n_seg_blocks) {
-        // ---- hub segment: one warp reduces kHubSegment arcs of a long row into a partial
-        const int64_t seg = a.seg_lo + (int64_t)blockIdx.x * kWarps + warp;
+        const int64_t seg = a.seg_lo + (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
         if (seg >= a.seg_hi) return;
         const int64_t beg = __ldg(a.seg_begin + seg), end = __ldg(a.seg_end + seg);
-        s.limit = end;
-        s.open(beg, lane);
+        const int64_t base = beg & ~int64_t(31);
+        s.span = a.colidx + base;
+        s.limit = (uint32_t)(end - base);
+        s.open((uint32_t)(beg - base), lane);
         float tot[VW];
-        reduce_arcs<LPR, VW, U>(s, beg, end, xcol, a.ldx, col_ok, lane, tot);
+        reduce_arcs<LPR, VW>(s, (uint32_t)(beg - base), s.limit, xcol, a.ldx, col_ok, lane,
+                             pol_hot, tot);
         if (col_ok && grp == 0) store_stream<VW>(a.partial + seg * a.d + col, tot, 1.f);
         return;
     }
 
-    // ---- ordinary rows: rows_per_warp consecutive rows per warp
-    const int64_t rb = (int64_t)blockIdx.x - a.n_seg_blocks;
-    const int64_t first = a.row_lo + (rb * kWarps + warp) * a.rows_per_warp;
+    const int64_t first = a.row_lo + (((int64_t)blockIdx.x - a.n_seg_blocks) * kWarps +
+                                      (threadIdx.x >> 5)) * a.rows_per_warp;
     if (first >= a.row_hi) return;
     const int nrows = (int)min((int64_t)a.rows_per_warp, a.row_hi - first);
-    const int64_t rp = lane <= nrows ? __ldg(a.rowptr + first + lane) : 0;
+    const int64_t rp64 = lane <= nrows ? __ldg(a.rowptr + first + lane) : 0;
+    // offsets are taken from the 32-aligned position at or below the span start, so chunk
+    // boundaries (and with them the summation order) depend on absolute arc positions only,
+    // not on how rows are grouped into warps or on the row range of the call
+    const int64_t span_beg = __shfl_sync(kFull, rp64, 0) & ~int64_t(31);
+    const uint32_t rp = (uint32_t)(rp64 - span_beg);   // span-relative row boundaries
+    s.span = a.colidx + span_beg;
     s.limit = __shfl_sync(kFull, rp, nrows);
     s.open(__shfl_sync(kFull, rp, 0), lane);
 
     for (int r = 0; r < nrows; ++r) {
-        const int64_t beg = __shfl_sync(kFull, rp, r);
-        const int64_t end = __shfl_sync(kFull, rp, r + 1);
-        const int64_t deg = end - beg;
-        if (deg > kHubThreshold) continue;  // produced by segment warps + hub_fixup_kernel
+        const uint32_t beg = __shfl_sync(kFull, rp, r);
+        const uint32_t end = __shfl_sync(kFull, rp, r + 1);
+        const uint32_t deg = end - beg;
+        if (deg > (uint32_t)kHubThreshold) continue;  // segment warps + hub_fixup_kernel
         float tot[VW];
-        reduce_arcs<LPR, VW, U>(s, beg, end, xcol, a.ldx, col_ok, lane, tot);
+        reduce_arcs<LPR, VW>(s, beg, end, xcol, a.ldx, col_ok, lane, pol_hot, tot);
         if (!col_ok) continue;
         const int64_t o = (first + r) * a.ldo + col;
         // lane group 0 writes the sum block, group 1 (or the same lanes when LPR == 32) the mean
         if (a.out_sum && grp == 0) store_stream<VW>(a.out_sum + o, tot, 1.f);
-        if (a.out_mean && grp == (G >= 2 ? 1 : 0)) {
-            float m[VW];
-#pragma unroll
-            for (int c = 0; c < VW; ++c) m[c] = deg > 0 ? tot[c] / (float)deg : 0.f;
-            store_stream<VW>(a.out_mean + o, m, 1.f);
-        }
+        if (a.out_mean && grp == (G >= 2 ? 1 : 0))
+            store_stream<VW>(a.out_mean + o, tot, deg ? __frcp_rn((float)deg) : 0.f);
     }
 }
 
@@ -230,21 +259,23 @@ hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict_
 }
 
 // ---- launch plumbing --------------------------------------------------------------------
-template <int LPR, int VW, int U>
-cudaError_t launch_gather(const RefexArgs& a, dim3 grid, cudaStream_t st) {
-    refex_gather_kernel<LPR, VW, U><<<grid, kWarps * 32, 0, st>>>(a);
+template <int LPR, int VW>
+cudaError_t launch_gather(const RefexArgs& a, dim3 row_grid, dim3 seg_grid, cudaStream_t st) {
+    dim3 grid(row_grid.x + seg_grid.x, row_grid.y, 1);
+    refex_gather_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a);
+    count_launch();
     return cudaGetLastError();
 }
 
-template <int VW, int U>
-cudaError_t dispatch_lpr(int lpr, const RefexArgs& a, dim3 grid, cudaStream_t st) {
+template <int VW>
+cudaError_t dispatch_lpr(int lpr, const RefexArgs& a, dim3 rg, dim3 sg, cudaStream_t st) {
     switch (lpr) {
-        case 1: return launch_gather<1, VW, U>(a, grid, st);
-        case 2: return launch_gather<2, VW, U>(a, grid, st);
-        case 4: return launch_gather<4, VW, U>(a, grid, st);
-        case 8: return launch_gather<8, VW, U>(a, grid, st);
-        case 16: return launch_gather<16, VW, U>(a, grid, st);
-        default: return launch_gather<32, VW, U>(a, grid, st);
+        case 1: return launch_gather<1, VW>(a, rg, sg, st);
+        case 2: return launch_gather<2, VW>(a, rg, sg, st);
+        case 4: return launch_gather<4, VW>(a, rg, sg, st);
+        case 8: return launch_gather<8, VW>(a, rg, sg, st);
+        case 16: return launch_gather<16, VW>(a, rg, sg, st);
+        default: return launch_gather<32, VW>(a, rg, sg, st);
     }
 }
 
@@ -301,7 +332,7 @@ extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, 
 
     RefexArgs a;
     a.rowptr = g->rowptr;
-    a.colidx = g->colidx;
+    a.colidx = g->d_colidx_tagged ? g->d_colidx_tagged : g->colidx;
     a.X = X;
     a.ldx = ldx;
     a.d = d;
@@ -316,7 +347,7 @@ extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, 
     a.seg_hi = seg_hi;
     a.partial = g->d_partial;
     a.n_seg_blocks = ceil_div<int64_t>(seg_hi - seg_lo, kWarps);
-    a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", 8, 1, 31);
+    a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", 16, 1, 31);
 
     const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) &&
                       (!out_sum || aligned16(out_sum)) && (!out_mean || aligned16(out_mean));
@@ -330,20 +361,11 @@ extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, 
         ceil_div<int64_t>(row_hi - row_lo, (int64_t)kWarps * a.rows_per_warp);
     GR_REQUIRE(row_blocks + a.n_seg_blocks < (int64_t)INT32_MAX && col_tiles <= 65535,
                "gr_refex_aggregate_f32: grid too large");
-    dim3 grid((unsigned)(row_blocks + a.n_seg_blocks), (unsigned)col_tiles, 1);
+    dim3 row_grid((unsigned)row_blocks, (unsigned)col_tiles, 1);
+    dim3 seg_grid((unsigned)a.n_seg_blocks, (unsigned)col_tiles, 1);
 
-    cudaError_t e;
-    if (vec4) {
-        switch (env_int("GR_REFEX_UNROLL", 4, 1, 8)) {
-            case 1: e = dispatch_lpr<4, 1>(lpr, a, grid, st); break;
-            case 2: e = dispatch_lpr<4, 2>(lpr, a, grid, st); break;
-            case 8: e = dispatch_lpr<4, 8>(lpr, a, grid, st); break;
-            default: e = dispatch_lpr<4, 4>(lpr, a, grid, st); break;
-        }
-    } else {
-        e = dispatch_lpr<1, 4>(lpr, a, grid, st);
-    }
-    count_launch();
+    cudaError_t e = vec4 ? dispatch_lpr<4>(lpr, a, row_grid, seg_grid, st)
+                         : dispatch_lpr<1>(lpr, a, row_grid, seg_grid, st);
     if (e != cudaSuccess)
         return fail(GR_ERR_CUDA, "refex_gather_kernel launch failed: %s", cudaGetErrorString(e));
 

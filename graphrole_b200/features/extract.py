@@ -172,6 +172,7 @@ def _aggregate_on_device(csr, X: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         return np.zeros((n, 0)), np.zeros((n, 0))
     handle = csr.handle()
     device = handle.device
+    X = np.ascontiguousarray(X)
     missing = np.isnan(X)
     if missing.any():
         # aggregate [values with NaN->0 | 1 where present]: mean = sum / count of present

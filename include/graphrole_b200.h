@@ -62,17 +62,27 @@ int64_t gr_kernel_launch_count(void);
  * rowptr  int64[n_rows + 1], rowptr[0] == 0, rowptr[n_rows] == nnz, non-decreasing
  * colidx  int32[nnz], values in [0, n_cols)
  * The arrays are NOT copied: they must stay valid and unchanged until gr_csr_destroy().
- * validate != 0 also range-checks colidx on the device (one extra pass over colidx).
+ * flags:
+ *   GR_CSR_VALIDATE   range-check colidx on the device (one extra pass over colidx)
+ *   GR_CSR_HOT_HINTS  build a library-owned copy of colidx (4*nnz bytes) whose sign bit marks
+ *                     arcs into the most frequently gathered rows (top rows by in-degree, as
+ *                     many as fit a fixed share of L2); the gather kernel loads those rows
+ *                     with an L2 evict_last policy.  Purely a cache hint: results are
+ *                     bit-identical with and without it.
+ * One stream per handle at a time: the handle's workspaces are reused by consecutive calls.
  */
 typedef struct gr_csr gr_csr_t;
 
+enum { GR_CSR_VALIDATE = 1, GR_CSR_HOT_HINTS = 2 };
+
 int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int64_t nnz,
                   const int64_t* rowptr_dev, const int32_t* colidx_dev,
-                  int device, int validate);
+                  int device, int flags);
 int gr_csr_destroy(gr_csr_t* g);
-/* n_rows, n_cols, nnz, number of hub rows (rows split across warps), number of hub segments */
+/* n_rows, n_cols, nnz, number of hub rows (rows split across warps), number of hub segments,
+ * number of rows tagged hot (0 without GR_CSR_HOT_HINTS) */
 int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
-                int64_t* n_hub_rows, int64_t* n_hub_segments);
+                int64_t* n_hub_rows, int64_t* n_hub_segments, int64_t* n_hot_rows);
 
 /* ---- path A: one ReFeX recursion level -------------------------------------------------
  * Replaces graphrole/features/extract.py:105-118 (reindex -> agg([sum, mean]) -> fillna(0))
@@ -83,7 +93,8 @@ int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nn
  * agg-major order (extract.py:158-162): pass out_mean = out_sum + d with ldo = 2*d to get the
  * reference's [c1(sum)..cd(sum), c1(mean)..cd(mean)] row layout in one buffer.
  * Either output pointer may be NULL to skip that aggregation.
- * fp32 storage; per-lane multi-accumulator fp32 sums, hub rows combined in fp64.
+ * fp32 storage; fp32 sums in 32/LPR independent lane-group accumulators per column (rows of at
+ * most 2048 arcs), hub rows combined from 1024-arc partials in fp64.
  * X must not alias the outputs.
  */
 int gr_refex_aggregate_f32(gr_csr_t* g, const float* X_dev, int64_t ldx, int32_t d,
