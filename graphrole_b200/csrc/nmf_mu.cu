@@ -1,17 +1,406 @@
-// Path B placeholder: replaced by the real kernels in the next milestone of this round.
+// Path B: RolX NMF, multiplicative updates for the Frobenius loss, on sm_100a.
+//
+// Replaces sklearn.decomposition._nmf._fit_multiplicative_update (beta_loss = 2, no
+// regularisation; sklearn/decomposition/_nmf.py:726-888) as reached from
+// graphrole/roles/factor.py:19-25.  One iteration is
+//     W <- W * (X H^T) / (W (H H^T))          (_nmf.py:535-549, :615-624)
+//     H <- H * (W^T X) / ((W^T W) H)          (_nmf.py:633-635, :701-721; uses the new W)
+// with exactly-zero denominators replaced by float32 eps (_nmf.py:32).
+//
+// This file holds the host loop, the small r x r / r x f kernels shared by both compute paths,
+// and the fp32 FFMA path (use_tf32 == 0, and the shapes the tcgen05 kernel does not take):
+//   nmf_update_w_kernel   X H^T per 64-row block with the W update fused in the epilogue
+//   nmf_wt_x_kernel       W^T X (and W^T W) as per-split partials, reduced in fixed order
+//   nmf_update_h_kernel   partial reduction + H update;   nmf_hht_kernel  H H^T
+//   nmf_error_kernel      ||X - W H||_F^2 from the dense residual (_nmf.py:122), fp64 sums
+// The tcgen05 / TMA fused single-pass kernel lives in nmf_mu_tc.cu.
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "common.cuh"
+#include "nmf_handle.cuh"
+
 using namespace gr;
-struct gr_nmf { int device; };
-extern "C" int gr_nmf_create(gr_nmf_t** out, int64_t, int32_t, int32_t, int) {
-    if (out) *out = nullptr;
-    return fail(GR_ERR_CUDA, "gr_nmf_*: kernels not built yet");
+
+namespace {
+
+constexpr float kEps = 1.1920928955078125e-07f;  // np.finfo(np.float32).eps, _nmf.py:32
+constexpr int kThreads = 256;
+constexpr int kBM = 64;  // rows per CTA tile in nmf_update_w_kernel
+constexpr int kBK = 32;  // K (feature) chunk
+
+// ---- H H^T (r x r), one CTA ----------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+nmf_hht_kernel(const float* __restrict__ H, int r, int f, float* __restrict__ HHt) {
+    const int i = threadIdx.x / 32, j = threadIdx.x % 32;
+    if (i >= r || j >= r) return;
+    float acc = 0.f;
+    for (int c = 0; c < f; ++c) acc = fmaf(H[(int64_t)i * f + c], H[(int64_t)j * f + c], acc);
+    HHt[i * r + j] = acc;
 }
-extern "C" int gr_nmf_destroy(gr_nmf_t*) { return GR_OK; }
-extern "C" int gr_nmf_mu_f32(gr_nmf_t*, const float*, int64_t, float*, float*, int32_t, double,
-                             int32_t, int32_t, int32_t*, double*, void*) {
-    return fail(GR_ERR_CUDA, "gr_nmf_*: kernels not built yet");
+
+// ---- W update: XHt tile on FFMA, epilogue W *= XHt / (W HHt) ----------------------------------
+template <int RP>
+__global__ void __launch_bounds__(kThreads)
+nmf_update_w_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f, int r,
+                    const float* __restrict__ H, const float* __restrict__ HHt,
+                    float* __restrict__ W) {
+    constexpr int RQ = RP / 4;  // roles per thread
+    __shared__ float Xs[kBM][kBK + 1];
+    __shared__ float Hs[RP][kBK + 1];
+    __shared__ float Ws[kBM][RP + 1];
+    __shared__ float HHts[RP][RP + 1];
+    const int tid = threadIdx.x;
+    const int row = tid / 4, rg = tid % 4;
+    const int64_t row0 = (int64_t)blockIdx.x * kBM;
+
+    for (int i = tid; i < RP * RP; i += kThreads) {
+        const int a = i / RP, b = i % RP;
+        HHts[a][b] = (a < r && b < r) ? HHt[a * r + b] : 0.f;
+    }
+    for (int i = tid; i < kBM * RP; i += kThreads) {
+        const int a = i / RP, b = i % RP;
+        Ws[a][b] = (row0 + a < n && b < r) ? W[(row0 + a) * r + b] : 0.f;
+    }
+
+    float acc[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) acc[j] = 0.f;
+
+    for (int k0 = 0; k0 < f; k0 += kBK) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kBM * kBK / kThreads; ++i) {
+            const int rr = i * (kThreads / kBK) + tid / kBK, cc = tid % kBK;
+            Xs[rr][cc] = (row0 + rr < n && k0 + cc < f) ? __ldg(X + (row0 + rr) * ldx + k0 + cc)
+                                                         : 0.f;
+        }
+        for (int i = tid; i < RP * kBK; i += kThreads) {
+            const int a = i / kBK, cc = i % kBK;
+            Hs[a][cc] = (a < r && k0 + cc < f) ? __ldg(H + (int64_t)a * f + k0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < kBK; ++kk) {
+            const float x = Xs[row][kk];
+#pragma unroll
+            for (int j = 0; j < RQ; ++j) acc[j] = fmaf(x, Hs[rg * RQ + j][kk], acc[j]);
+        }
+    }
+    if (row0 + row >= n) return;
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) {
+        const int role = rg * RQ + j;
+        if (role >= r) continue;
+        float den = 0.f;
+        for (int l = 0; l < r; ++l) den = fmaf(Ws[row][l], HHts[l][role], den);
+        if (den == 0.f) den = kEps;
+        W[(row0 + row) * r + role] = Ws[row][role] * (acc[j] / den);
+    }
 }
-extern "C" int gr_nmf_error_f32(gr_nmf_t*, const float*, int64_t, const float*, const float*,
-                                double*, void*) {
-    return fail(GR_ERR_CUDA, "gr_nmf_*: kernels not built yet");
+
+// ---- partial W^T M for a row-major M [n, fc] (M = X gives W^T X, M = W gives W^T W) -----------
+// grid: (column slabs of kThreads, row splits).  out[(split * RP + l) * fc + col]
+template <int RP>
+__global__ void __launch_bounds__(kThreads)
+nmf_wt_x_kernel(const float* __restrict__ M, int64_t ldm, int64_t n, int fc,
+                const float* __restrict__ W, int r, int64_t rows_per_split,
+                float* __restrict__ out) {
+    constexpr int RB = 32;  // rows staged per step
+    __shared__ float Ws[RB][RP];
+    const int col = blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_hi = min(n, r_lo + rows_per_split);
+    float acc[RP];
+#pragma unroll
+    for (int l = 0; l < RP; ++l) acc[l] = 0.f;
+
+    for (int64_t b = r_lo; b < r_hi; b += RB) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < RB * RP; i += kThreads) {
+            const int a = i / RP, l = i % RP;
+            Ws[a][l] = (b + a < r_hi && l < r) ? __ldg(W + (b + a) * r + l) : 0.f;
+        }
+        __syncthreads();
+        if (col < fc) {
+            const int cnt = (int)min((int64_t)RB, r_hi - b);
+            float x[8];
+            for (int a0 = 0; a0 < cnt; a0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    x[u] = a0 + u < cnt ? __ldg(M + (b + a0 + u) * ldm + col) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int l = 0; l < RP; ++l) acc[l] = fmaf(Ws[a0 + u][l], x[u], acc[l]);
+            }
+        }
+    }
+    if (col < fc)
+#pragma unroll
+        for (int l = 0; l < RP; ++l)
+            if (l < r) out[((int64_t)blockIdx.y * RP + l) * fc + col] = acc[l];
+}
+
+// ---- fixed-order reduction of the W^T W partials (r x r) --------------------------------------
+__global__ void __launch_bounds__(1024)
+nmf_reduce_wtw_kernel(const float* __restrict__ part, int splits, int rp, int r,
+                      float* __restrict__ WtW) {
+    const int i = threadIdx.x / 32, j = threadIdx.x % 32;
+    if (i >= r || j >= r) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * rp + i) * r + j];
+    WtW[i * r + j] = acc;
+}
+
+// ---- H update: reduce W^T X partials, H_next = H * WtX / (WtW H) --------------------------------
+// One thread per (role, column): grid (column slabs, r).  Reads the old H, writes H_next (the
+// caller copies it back), so no thread sees a half-updated column.
+__global__ void __launch_bounds__(kThreads)
+nmf_update_h_kernel(const float* __restrict__ part, int splits, int rp, int r, int f,
+                    const float* __restrict__ WtW, const float* __restrict__ H,
+                    float* __restrict__ H_next) {
+    const int col = blockIdx.x * kThreads + threadIdx.x;
+    const int l = blockIdx.y;
+    if (col >= f) return;
+    float num = 0.f;
+    for (int s = 0; s < splits; ++s) num += part[((int64_t)s * rp + l) * f + col];  // fixed order
+    float den = 0.f;
+    for (int m = 0; m < r; ++m) den = fmaf(__ldg(WtW + l * r + m), H[(int64_t)m * f + col], den);
+    if (den == 0.f) den = kEps;
+    H_next[(int64_t)l * f + col] = H[(int64_t)l * f + col] * (num / den);
+}
+
+// ---- ||X - W H||_F^2 partials: thread per column, fp64 accumulation ----------------------------
+template <int RP>
+__global__ void __launch_bounds__(kThreads)
+nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
+                 const float* __restrict__ W, const float* __restrict__ H, int r,
+                 int64_t rows_per_split, double* __restrict__ out) {
+    constexpr int RB = 32;
+    __shared__ float Ws[RB][RP];
+    __shared__ double red[kThreads / 32];
+    const int col = blockIdx.x * kThreads + threadIdx.x;
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_hi = min(n, r_lo + rows_per_split);
+    float h[RP];
+#pragma unroll
+    for (int l = 0; l < RP; ++l) h[l] = (l < r && col < f) ? __ldg(H + (int64_t)l * f + col) : 0.f;
+    double total = 0.0;
+    for (int64_t b = r_lo; b < r_hi; b += RB) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < RB * RP; i += kThreads) {
+            const int a = i / RP, l = i % RP;
+            Ws[a][l] = (b + a < r_hi && l < r) ? __ldg(W + (b + a) * r + l) : 0.f;
+        }
+        __syncthreads();
+        if (col < f) {
+            const int cnt = (int)min((int64_t)RB, r_hi - b);
+            float part = 0.f;
+            for (int a = 0; a < cnt; ++a) {
+                float wh = 0.f;
+#pragma unroll
+                for (int l = 0; l < RP; ++l) wh = fmaf(Ws[a][l], h[l], wh);
+                const float diff = __ldg(X + (b + a) * ldx + col) - wh;
+                part = fmaf(diff, diff, part);
+            }
+            total += (double)part;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+        out[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+template <typename F>
+int dispatch_rp(int rp, F&& fn) {
+    switch (rp) {
+        case 8: return fn(std::integral_constant<int, 8>{});
+        case 16: return fn(std::integral_constant<int, 16>{});
+        default: return fn(std::integral_constant<int, 32>{});
+    }
+}
+
+#define GR_LAUNCH_CHECK(name)                                                              \
+    do {                                                                                   \
+        count_launch();                                                                    \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return fail(GR_ERR_CUDA, "%s launch failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+int launch_hht(gr_nmf* h, const float* H, cudaStream_t st) {
+    nmf_hht_kernel<<<1, 1024, 0, st>>>(H, h->r, h->f, h->d_hht);
+    GR_LAUNCH_CHECK("nmf_hht_kernel");
+    return GR_OK;
+}
+
+}  // namespace
+
+// ---- FFMA path: one multiplicative-update iteration --------------------------------------------
+int gr::nmf_iteration_fma(gr_nmf* h, const float* X, int64_t ldx, float* W, float* H,
+                          cudaStream_t st) {
+    const int r = h->r, f = h->f, rp = h->rp;
+    const int64_t n = h->n;
+    if (int rc = launch_hht(h, H, st)) return rc;
+    if (int rc = dispatch_rp(rp, [&](auto RPc) {
+            constexpr int RP = decltype(RPc)::value;
+            nmf_update_w_kernel<RP><<<(unsigned)ceil_div<int64_t>(n, kBM), kThreads, 0, st>>>(
+                X, ldx, n, f, r, H, h->d_hht, W);
+            GR_LAUNCH_CHECK("nmf_update_w_kernel");
+            dim3 gx((unsigned)ceil_div(f, kThreads), (unsigned)h->splits);
+            nmf_wt_x_kernel<RP><<<gx, kThreads, 0, st>>>(X, ldx, n, f, W, r, h->rows_per_split,
+                                                        h->d_part_wtx);
+            GR_LAUNCH_CHECK("nmf_wt_x_kernel(X)");
+            dim3 gw(1, (unsigned)h->splits);
+            nmf_wt_x_kernel<RP><<<gw, kThreads, 0, st>>>(W, r, n, r, W, r, h->rows_per_split,
+                                                        h->d_part_wtw);
+            GR_LAUNCH_CHECK("nmf_wt_x_kernel(W)");
+            return (int)GR_OK;
+        }))
+        return rc;
+    return nmf_finish_iteration(h, H, st);
+}
+
+// Shared tail of an iteration: reduce the partials, update H.
+int gr::nmf_finish_iteration(gr_nmf* h, float* H, cudaStream_t st) {
+    nmf_reduce_wtw_kernel<<<1, 1024, 0, st>>>(h->d_part_wtw, h->splits, h->rp, h->r, h->d_wtw);
+    GR_LAUNCH_CHECK("nmf_reduce_wtw_kernel");
+    dim3 grid((unsigned)ceil_div(h->f, kThreads), (unsigned)h->r);
+    nmf_update_h_kernel<<<grid, kThreads, 0, st>>>(h->d_part_wtx, h->splits, h->rp, h->r, h->f,
+                                                 h->d_wtw, H, h->d_h_next);
+    GR_LAUNCH_CHECK("nmf_update_h_kernel");
+    GR_CUDA_TRY(cudaMemcpyAsync(H, h->d_h_next, (size_t)h->r * h->f * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    return GR_OK;
+}
+
+int gr::nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const float* H,
+                  double* err, cudaStream_t st) {
+    const int slabs = ceil_div(h->f, kThreads);
+    if (int rc = dispatch_rp(h->rp, [&](auto RPc) {
+            constexpr int RP = decltype(RPc)::value;
+            dim3 g((unsigned)slabs, (unsigned)h->splits);
+            nmf_error_kernel<RP><<<g, kThreads, 0, st>>>(X, ldx, h->n, h->f, W, H, h->r,
+                                                        h->rows_per_split, h->d_err_part);
+            GR_LAUNCH_CHECK("nmf_error_kernel");
+            return (int)GR_OK;
+        }))
+        return rc;
+    const size_t cnt = (size_t)slabs * h->splits;
+    h->h_err_part.resize(cnt);
+    GR_CUDA_TRY(cudaMemcpyAsync(h->h_err_part.data(), h->d_err_part, cnt * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    double total = 0.0;
+    for (size_t i = 0; i < cnt; ++i) total += h->h_err_part[i];  // fixed order
+    *err = std::sqrt(total);
+    return GR_OK;
+}
+
+// ---- C-ABI --------------------------------------------------------------------------------------
+extern "C" int gr_nmf_create(gr_nmf_t** out, int64_t n, int32_t f, int32_t r, int device) {
+    GR_REQUIRE(out != nullptr, "gr_nmf_create: out is NULL");
+    *out = nullptr;
+    GR_REQUIRE(n >= 1 && f >= 1 && r >= 1, "gr_nmf_create: n, f, r must be positive");
+    GR_REQUIRE(r <= 32, "gr_nmf_create: n_roles = %d not supported (r <= 32)", r);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "gr_nmf_create: cannot select device %d", device);
+    if (int rc = require_sm100(device)) return rc;
+
+    gr_nmf* h = new (std::nothrow) gr_nmf();
+    if (!h) return fail(GR_ERR_OUT_OF_MEMORY, "gr_nmf_create: host allocation failed");
+    h->device = device;
+    h->n = n;
+    h->f = f;
+    h->r = r;
+    h->rp = r <= 8 ? 8 : (r <= 16 ? 16 : 32);
+    // row splits of the W^T X / error kernels: enough CTAs to fill the GPU, >= 256 rows each
+    const int slabs = ceil_div(f, kThreads);
+    const int64_t want = std::max<int64_t>(1, (148 * 4) / slabs);
+    h->splits = (int)std::max<int64_t>(1, std::min<int64_t>(want, ceil_div<int64_t>(n, 256)));
+    h->rows_per_split = ceil_div<int64_t>(ceil_div<int64_t>(n, h->splits), 32) * 32;
+    h->splits = (int)ceil_div<int64_t>(n, h->rows_per_split);
+
+    auto alloc = [&](auto** p, size_t count) {
+        return cudaMalloc(p, count * sizeof(**p)) == cudaSuccess;
+    };
+    const bool ok = alloc(&h->d_hht, (size_t)r * r) && alloc(&h->d_wtw, (size_t)r * r) &&
+                    alloc(&h->d_h_next, (size_t)r * f) &&
+                    alloc(&h->d_part_wtx, (size_t)h->splits * h->rp * f) &&
+                    alloc(&h->d_part_wtw, (size_t)h->splits * h->rp * r) &&
+                    alloc(&h->d_err_part, (size_t)slabs * h->splits);
+    if (!ok) {
+        cudaGetLastError();
+        gr_nmf_destroy(h);
+        return fail(GR_ERR_OUT_OF_MEMORY, "gr_nmf_create: device allocation failed");
+    }
+    *out = h;
+    return GR_OK;
+}
+
+extern "C" int gr_nmf_destroy(gr_nmf_t* h) {
+    if (!h) return GR_OK;
+    DeviceGuard guard(h->device);
+    cudaFree(h->d_hht);
+    cudaFree(h->d_wtw);
+    cudaFree(h->d_h_next);
+    cudaFree(h->d_part_wtx);
+    cudaFree(h->d_part_wtw);
+    cudaFree(h->d_err_part);
+    nmf_tc_release(h);
+    delete h;
+    return GR_OK;
+}
+
+extern "C" int gr_nmf_error_f32(gr_nmf_t* h, const float* X, int64_t ldx, const float* W,
+                                const float* H, double* err_out, void* stream) {
+    GR_REQUIRE(h && X && W && H && err_out, "gr_nmf_error_f32: NULL argument");
+    GR_REQUIRE(ldx >= h->f, "gr_nmf_error_f32: ldx < f");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    return nmf_error(h, X, ldx, W, H, err_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gr_nmf_mu_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W, float* H,
+                             int32_t max_iter, double tol, int32_t check_every, int32_t use_tf32,
+                             int32_t* n_iter_out, double* err_out, void* stream) {
+    GR_REQUIRE(h && X && W && H, "gr_nmf_mu_f32: NULL argument");
+    GR_REQUIRE(ldx >= h->f, "gr_nmf_mu_f32: ldx = %lld < f = %d", (long long)ldx, h->f);
+    GR_REQUIRE(max_iter >= 0 && tol >= 0 && check_every >= 1, "gr_nmf_mu_f32: bad loop control");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const bool tc = use_tf32 && nmf_tc_supported(h, X, ldx);
+    double error_at_init = 0.0, previous = 0.0, error = 0.0;
+    if (tol > 0) {
+        if (int rc = nmf_error(h, X, ldx, W, H, &error_at_init, st)) return rc;
+        previous = error = error_at_init;
+    }
+    int it = 0;
+    for (it = 1; it <= max_iter; ++it) {
+        if (int rc = tc ? nmf_iteration_tc(h, X, ldx, W, H, st)
+                        : nmf_iteration_fma(h, X, ldx, W, H, st))
+            return rc;
+        if (tol > 0 && it % check_every == 0) {
+            if (int rc = nmf_error(h, X, ldx, W, H, &error, st)) return rc;
+            if ((previous - error) / error_at_init < tol) break;   // _nmf.py:877
+            previous = error;
+        }
+    }
+    if (it > max_iter) it = max_iter;
+    if (tol == 0 && err_out)   // no convergence test ran: report the final error
+        if (int rc = nmf_error(h, X, ldx, W, H, &error, st)) return rc;
+    if (n_iter_out) *n_iter_out = it;
+    if (err_out) *err_out = error;
+    h->last_path_tc = tc;
+    return GR_OK;
 }

@@ -1,0 +1,159 @@
+"""Parity of hot path B (NMF multiplicative updates) on the GPU against scikit-learn.
+
+The reference's tests pin shapes and non-negativity only (tests/test_roles/test_factor.py:17-25);
+numerical parity is therefore anchored on scikit-learn -- the owner of the arithmetic -- with a
+SHARED start (init='custom' semantics): committed golden vectors (tests/golden/nmf_cases.npz),
+the pinned NumPy oracle, and the installed sklearn run live.
+
+Stated tolerances (fp32 storage on the GPU vs float64 in sklearn):
+  FFMA path (use_tf32=False)   factors after a fixed 50 iterations within 2e-3 relative to the
+                               factor's max entry; reconstruction error within 1e-4 relative
+  TF32 path (use_tf32=True)    factors within 2e-2 relative to max entry; error within 1e-3
+  stopping iteration           identical, or off by one convergence check (10 iterations) when
+                               sklearn's criterion is within rounding of the threshold
+"""
+import numpy as np
+import pytest
+import torch
+
+from graphrole_b200 import RoleExtractor
+from graphrole_b200.roles import factor
+from oracle import nmf_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = [('rand20x30', 2), ('rand20x30', 4), ('rand20x30', 7), ('rand300x64', 4),
+         ('rand300x64', 8), ('rand300x64', 16), ('planted500x48', 4), ('planted500x48', 8)]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device='cuda:0')
+
+
+def rel_to_max(got, ref):
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+@pytest.mark.parametrize('use_tf32,tol_f,tol_e', [(False, 2e-3, 1e-4), (True, 2e-2, 1e-3)])
+@pytest.mark.parametrize('name,r', CASES)
+def test_fixed_iterations_match_sklearn_golden(nmf_cases, name, r, use_tf32, tol_f, tol_e):
+    z = nmf_cases
+    X, W0, H0 = z[f'{name}__X'], z[f'{name}__r{r}__W0'], z[f'{name}__r{r}__H0']
+    W, H, n_iter, err = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=50, tol=0,
+                                      use_tf32=use_tf32)
+    assert n_iter == 50
+    W, H = W.cpu().numpy().astype(np.float64), H.cpu().numpy().astype(np.float64)
+    assert (W >= 0).all() and (H >= 0).all()
+    assert rel_to_max(W, z[f'{name}__r{r}__W50']) < tol_f
+    assert rel_to_max(H, z[f'{name}__r{r}__H50']) < tol_f
+    ref_err = oracle.frobenius_error(X, z[f'{name}__r{r}__W50'], z[f'{name}__r{r}__H50'])
+    assert err == pytest.approx(ref_err, rel=tol_e)
+    assert err == pytest.approx(oracle.frobenius_error(X, W, H), rel=1e-4)
+
+
+@pytest.mark.parametrize('name,r', CASES)
+def test_convergence_loop_matches_sklearn(nmf_cases, name, r):
+    """tol = 1e-4, max_iter = 200, check every 10 iterations (sklearn NMF defaults)."""
+    z = nmf_cases
+    X, W0, H0 = z[f'{name}__X'], z[f'{name}__r{r}__W0'], z[f'{name}__r{r}__H0']
+    W, H, n_iter, err = factor.nmf_mu(dev(X), dev(W0), dev(H0), use_tf32=False)
+    ref_iter = int(z[f'{name}__r{r}__n_iter'])
+    assert abs(n_iter - ref_iter) <= 10 and n_iter % 10 == 0
+    ref_err = float(z[f'{name}__r{r}__err'])
+    assert err == pytest.approx(ref_err, rel=2e-3)
+    if n_iter == ref_iter:
+        assert rel_to_max(W.cpu().numpy(), z[f'{name}__r{r}__Wconv']) < 5e-3
+        assert rel_to_max(H.cpu().numpy(), z[f'{name}__r{r}__Hconv']) < 5e-3
+
+
+def test_against_oracle_and_live_sklearn_medium():
+    sk = pytest.importorskip('sklearn.decomposition._nmf')
+    rng = np.random.RandomState(7)
+    n, f, r = 5000, 96, 12
+    X = rng.rand(n, 8) @ rng.rand(8, f) + 0.05 * rng.rand(n, f)
+    W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+    W_sk, H_sk, _ = sk._fit_multiplicative_update(X, W0.copy(), H0.copy(), 'frobenius',
+                                                  max_iter=30, tol=0)
+    W_or, H_or, _ = oracle.fit_multiplicative_update(X, W0, H0, max_iter=30, tol=0)
+    np.testing.assert_allclose(W_or, W_sk, rtol=1e-9)
+    W, H, _, err = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=30, tol=0, use_tf32=False)
+    assert rel_to_max(W.cpu().numpy(), W_sk) < 2e-3
+    assert rel_to_max(H.cpu().numpy(), H_sk) < 2e-3
+    assert err == pytest.approx(oracle.frobenius_error(X, W_sk, H_sk), rel=1e-4)
+    assert factor.nmf_error(dev(X), dev(W_sk), dev(H_sk)) == pytest.approx(
+        oracle.frobenius_error(X, W_sk, H_sk), rel=1e-5)
+
+
+def test_zero_denominators_and_edge_shapes():
+    X = np.array([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 0.0]])
+    W0 = np.array([[1.0, 0.0], [0.0, 0.0], [0.0, 0.0]])
+    H0 = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    W, H, _, _ = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=5, tol=0, use_tf32=False)
+    Wr, Hr, _ = oracle.fit_multiplicative_update(X, W0, H0, max_iter=5, tol=0)
+    assert torch.isfinite(W).all() and torch.isfinite(H).all()
+    np.testing.assert_allclose(W.cpu().numpy(), Wr, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(H.cpu().numpy(), Hr, rtol=1e-4, atol=1e-7)
+    # single row / single feature / rank 1, odd sizes
+    rng = np.random.RandomState(1)
+    for n, f, r in [(1, 5, 1), (7, 1, 1), (65, 33, 3), (257, 513, 5), (1000, 7, 7)]:
+        X = rng.rand(n, f)
+        W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+        W, H, _, _ = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=10, tol=0, use_tf32=False)
+        Wr, Hr, _ = oracle.fit_multiplicative_update(X, W0, H0, max_iter=10, tol=0)
+        assert rel_to_max(W.cpu().numpy(), Wr) < 1e-3
+        assert rel_to_max(H.cpu().numpy(), Hr) < 1e-3
+    with pytest.raises(ValueError):
+        factor.nmf_mu(dev(rng.rand(50, 40)), dev(rng.rand(50, 33)), dev(rng.rand(33, 40)))
+
+
+def test_get_nmf_decomposition_contract():
+    """The reference's own test (tests/test_roles/test_factor.py:17-25): shapes, non-negative."""
+    np.random.seed(0)
+    X = np.random.rand(20, 30)
+    for n_roles in range(2, 8):
+        G, F = factor.get_nmf_decomposition(X, n_roles)
+        assert G.shape == (20, n_roles) and F.shape == (n_roles, 30)
+        assert (G >= 0).all() and (F >= 0).all()
+        assert G.dtype == np.float64
+    # quality: reconstruction error no worse than sklearn's from its own NNDSVDa start (+2 %)
+    from sklearn.decomposition import NMF
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for n_roles in (3, 6):
+            np.random.seed(1)
+            G, F = factor.get_nmf_decomposition(X, n_roles)
+            np.random.seed(1)
+            model = NMF(n_components=n_roles, solver='mu', init='nndsvda')
+            Gs = model.fit_transform(X)
+            ours = np.linalg.norm(X - G @ F)
+            theirs = np.linalg.norm(X - Gs @ model.components_)
+            assert ours <= theirs * 1.02
+
+
+def test_nndsvda_init_matches_sklearn_on_separated_spectrum():
+    sk = pytest.importorskip('sklearn.decomposition._nmf')
+    rng = np.random.RandomState(0)
+    X = (rng.rand(400, 4) * np.array([8.0, 4.0, 2.0, 1.0])) @ rng.rand(4, 60)
+    np.random.seed(3)
+    W_ref, H_ref = sk._initialize_nmf(X, 3, init='nndsvda')
+    np.random.seed(3)
+    W, H = factor.nndsvda_init(dev(X), 3)
+    np.testing.assert_allclose(W.cpu().numpy(), W_ref, rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(H.cpu().numpy(), H_ref, rtol=2e-4, atol=1e-5)
+
+
+def test_role_extractor_end_to_end(refex_cases):
+    """RoleExtractor surface on the karate features (tests/test_roles/test_extract.py:38-75)."""
+    from helpers import frame_from_json
+    feats = frame_from_json(refex_cases['karate']['features'])
+    rx = RoleExtractor(n_roles=3)
+    rx.extract_role_factors(feats)
+    assert rx.node_role_factor.shape == (34, 3)
+    assert rx.role_feature_factor.shape == (3, feats.shape[1])
+    assert list(rx.node_role_factor.columns) == ['role_0', 'role_1', 'role_2']
+    assert set(rx.roles.keys()) == set(feats.index)
+    np.testing.assert_allclose(rx.role_percentage.sum(axis=1).values, 1.0)
+    rx = RoleExtractor(n_roles=None, n_role_range=(2, 4), n_bit_range=(2, 4))
+    rx.extract_role_factors(feats)
+    assert 2 <= rx.node_role_factor.shape[1] <= 4
