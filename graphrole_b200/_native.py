@@ -38,6 +38,7 @@ SIGNATURES = {
     'gr_nmf_destroy': (c_int, [c_void_p]),
     'gr_nmf_mu_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_double,
                               c_int32, c_int32, POINTER(c_int32), POINTER(c_double), c_void_p]),
+    'gr_nmf_last_path': (c_int, [c_void_p]),
     'gr_nmf_error_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  POINTER(c_double), c_void_p]),
 }

@@ -27,7 +27,10 @@ struct gr_nmf {
 namespace gr {
 
 int nmf_iteration_fma(gr_nmf* h, const float* X, int64_t ldx, float* W, float* H, cudaStream_t st);
-int nmf_finish_iteration(gr_nmf* h, float* H, cudaStream_t st);
+int nmf_hht(gr_nmf* h, const float* H, cudaStream_t st);
+// Shared tail of an iteration: reduce [splits, rp, *] partials in fixed order, update H.
+int nmf_finish_iteration(gr_nmf* h, const float* part_wtx, const float* part_wtw, int splits,
+                         int rp, float* H, cudaStream_t st);
 int nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const float* H, double* err,
               cudaStream_t st);
 

@@ -236,20 +236,20 @@ int dispatch_rp(int rp, F&& fn) {
             return fail(GR_ERR_CUDA, "%s launch failed: %s", name, cudaGetErrorString(_e)); \
     } while (0)
 
-int launch_hht(gr_nmf* h, const float* H, cudaStream_t st) {
+}  // namespace
+
+int gr::nmf_hht(gr_nmf* h, const float* H, cudaStream_t st) {
     nmf_hht_kernel<<<1, 1024, 0, st>>>(H, h->r, h->f, h->d_hht);
     GR_LAUNCH_CHECK("nmf_hht_kernel");
     return GR_OK;
 }
-
-}  // namespace
 
 // ---- FFMA path: one multiplicative-update iteration --------------------------------------------
 int gr::nmf_iteration_fma(gr_nmf* h, const float* X, int64_t ldx, float* W, float* H,
                           cudaStream_t st) {
     const int r = h->r, f = h->f, rp = h->rp;
     const int64_t n = h->n;
-    if (int rc = launch_hht(h, H, st)) return rc;
+    if (int rc = nmf_hht(h, H, st)) return rc;
     if (int rc = dispatch_rp(rp, [&](auto RPc) {
             constexpr int RP = decltype(RPc)::value;
             nmf_update_w_kernel<RP><<<(unsigned)ceil_div<int64_t>(n, kBM), kThreads, 0, st>>>(
@@ -266,16 +266,17 @@ int gr::nmf_iteration_fma(gr_nmf* h, const float* X, int64_t ldx, float* W, floa
             return (int)GR_OK;
         }))
         return rc;
-    return nmf_finish_iteration(h, H, st);
+    return nmf_finish_iteration(h, h->d_part_wtx, h->d_part_wtw, h->splits, h->rp, H, st);
 }
 
 // Shared tail of an iteration: reduce the partials, update H.
-int gr::nmf_finish_iteration(gr_nmf* h, float* H, cudaStream_t st) {
-    nmf_reduce_wtw_kernel<<<1, 1024, 0, st>>>(h->d_part_wtw, h->splits, h->rp, h->r, h->d_wtw);
+int gr::nmf_finish_iteration(gr_nmf* h, const float* part_wtx, const float* part_wtw, int splits,
+                             int rp, float* H, cudaStream_t st) {
+    nmf_reduce_wtw_kernel<<<1, 1024, 0, st>>>(part_wtw, splits, rp, h->r, h->d_wtw);
     GR_LAUNCH_CHECK("nmf_reduce_wtw_kernel");
     dim3 grid((unsigned)ceil_div(h->f, kThreads), (unsigned)h->r);
-    nmf_update_h_kernel<<<grid, kThreads, 0, st>>>(h->d_part_wtx, h->splits, h->rp, h->r, h->f,
-                                                 h->d_wtw, H, h->d_h_next);
+    nmf_update_h_kernel<<<grid, kThreads, 0, st>>>(part_wtx, splits, rp, h->r, h->f, h->d_wtw, H,
+                                                 h->d_h_next);
     GR_LAUNCH_CHECK("nmf_update_h_kernel");
     GR_CUDA_TRY(cudaMemcpyAsync(H, h->d_h_next, (size_t)h->r * h->f * sizeof(float),
                                 cudaMemcpyDeviceToDevice, st));
@@ -359,6 +360,8 @@ extern "C" int gr_nmf_destroy(gr_nmf_t* h) {
     delete h;
     return GR_OK;
 }
+
+extern "C" int gr_nmf_last_path(const gr_nmf_t* h) { return h && h->last_path_tc ? 1 : 0; }
 
 extern "C" int gr_nmf_error_f32(gr_nmf_t* h, const float* X, int64_t ldx, const float* W,
                                 const float* H, double* err_out, void* stream) {

@@ -20,6 +20,8 @@ from graphrole_b200.types import FactorTuple
 MAX_ITER = 200
 TOL = 1e-4
 CHECK_EVERY = 10
+# which kernels the most recent nmf_mu call ran: 'tcgen05' or 'ffma'
+last_path = None
 
 
 def get_nmf_decomposition(X: np.ndarray, n_roles: int) -> FactorTuple:
@@ -72,6 +74,8 @@ def nmf_mu(X: torch.Tensor, W0: torch.Tensor, H0: torch.Tensor, max_iter: int = 
                 c_void_p(H.data_ptr()), max_iter, float(tol), check_every,
                 1 if use_tf32 else 0, byref(n_iter), byref(err), _native._stream_ptr(stream)),
                 'gr_nmf_mu_f32')
+            global last_path
+            last_path = 'tcgen05' if lib.gr_nmf_last_path(handle) else 'ffma'
         finally:
             lib.gr_nmf_destroy(handle)
     return W, H, int(n_iter.value), float(err.value)
