@@ -31,14 +31,22 @@ constexpr int kThreads = 256;
 constexpr int kBM = 64;  // rows per CTA tile in nmf_update_w_kernel
 constexpr int kBK = 32;  // K (feature) chunk
 
-// ---- H H^T (r x r), one CTA ----------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+// ---- H H^T (r x r): one CTA per row i, 8 column slices per output, fixed-order combine ----------
+__global__ void __launch_bounds__(256)
 nmf_hht_kernel(const float* __restrict__ H, int r, int f, float* __restrict__ HHt) {
-    const int i = threadIdx.x / 32, j = threadIdx.x % 32;
-    if (i >= r || j >= r) return;
+    __shared__ float part[8][33];
+    const int i = blockIdx.x, j = threadIdx.x % 32, slice = threadIdx.x / 32;
     float acc = 0.f;
-    for (int c = 0; c < f; ++c) acc = fmaf(H[(int64_t)i * f + c], H[(int64_t)j * f + c], acc);
-    HHt[i * r + j] = acc;
+    if (j < r)
+        for (int c = slice; c < f; c += 8)
+            acc = fmaf(H[(int64_t)i * f + c], H[(int64_t)j * f + c], acc);
+    part[slice][j] = acc;
+    __syncthreads();
+    if (slice == 0 && j < r) {
+        float t = 0.f;
+        for (int s = 0; s < 8; ++s) t += part[s][j];
+        HHt[i * r + j] = t;
+    }
 }
 
 // ---- W update: XHt tile on FFMA, epilogue W *= XHt / (W HHt) ----------------------------------
@@ -239,7 +247,7 @@ int dispatch_rp(int rp, F&& fn) {
 }  // namespace
 
 int gr::nmf_hht(gr_nmf* h, const float* H, cudaStream_t st) {
-    nmf_hht_kernel<<<1, 1024, 0, st>>>(H, h->r, h->f, h->d_hht);
+    nmf_hht_kernel<<<h->r, 256, 0, st>>>(H, h->r, h->f, h->d_hht);
     GR_LAUNCH_CHECK("nmf_hht_kernel");
     return GR_OK;
 }

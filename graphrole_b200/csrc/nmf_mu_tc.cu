@@ -6,8 +6,8 @@
 //   P1  XHt[64, 32]      = X_b (64 x f, K-major)  .  H^T      tcgen05.mma M=64  N=32 K=8 x f/8
 //   E   W_b             *= XHt / (W_b (H H^T))               epilogue warps: tcgen05.ld, fp32 math,
 //                                                            W_b -> global, tf32(W_b)^T -> smem
-//   P2  (W^T X)^T[f, 32] += X_b^T (MN-major)     .  W_b      tcgen05.mma M=128 N=32 K=8 x 8 per
-//                                                            128 columns; accumulators stay in TMEM
+//   P2  (W^T X)^T[f, 32] += X_b^T (MN-major)     .  W_b      tcgen05.mma M=64  N=32 K=8 x 8 per
+//                                                            64 columns; accumulators stay in TMEM
 //       (W^T W)[32, 32]  += W_b^T                 .  W_b      tcgen05.mma M=64  N=32 K=8 x 8
 // The accumulators of P2 live in TMEM for the whole kernel and are written once per CTA as
 // partials; nmf_finish_iteration (nmf_mu.cu) reduces them in fixed order and updates H.
@@ -17,14 +17,28 @@
 // tcgen05 requires for MN-major tf32 operands; P1 uses the ordinary 128B swizzle (K-major).
 // Algorithmic bytes per iteration: n*f*4 + 2*n*r*4.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
-// (TMEM lane quarter = warp_id % 4).  Software pipeline of the MMA warp:
-//   P1(0); then for i >= 1: P1(i), P2(i-1); finally P2(last)     -- the epilogue of block i-1
-// overlaps P1(i).  The shared-memory ring holds stages of 64 rows x 128 columns (4 TMA boxes).
+// Warp roles (224 threads): warp 0 = TMA producer of the P1 stream (HBM), warp 1 = MMA issuer,
+// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4), warp 6 = TMA producer of the P2
+// stream (L2 re-reads).  Each stream has its own shared-memory ring: P1 in 32 KB stages (four
+// 64 x 32 boxes = 128 columns under one mbarrier), P2 in 16 KB stages (two boxes = the 64
+// columns of one UMMA M tile).  MMA issue order: P1(0); then P1(i), P2(i-1) for i >= 1; finally
+// P2(last) -- the epilogue of block i-1 overlaps P1(i) and the P1 ring keeps prefetching from
+// HBM during P2(i-1).
+//
+// What was measured on B200 while getting here (profiles/README.md, C5 = 10 M x 512, r = 32):
+//   * one in-order ring of 4 x 32 KB shared by both phases: 9.1 ms / iteration (both load
+//     latencies exposed every block);
+//   * per-box (8 KB) mbarrier stages: a single-thread producer/consumer handshake costs ~500
+//     cycles, which caps a stream at ~4.4 TB/s regardless of ring depth; 32 KB per barrier
+//     streams at 6.6-7.4 TB/s with only 3 stages (tools/exp_tma.cu);
+//   * scalar per-row W loads/stores in the epilogue (16 rows x 4 B per warp instruction) cost
+//     ~5 us per block; the W tile of a warp is contiguous in memory, so it is staged through
+//     shared memory with coalesced 16-byte accesses instead.
 
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "nmf_handle.cuh"
@@ -33,34 +47,43 @@ using namespace gr;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;
 constexpr int kBlockRows = 64;      // rows of X per block (UMMA M of P1)
 constexpr int kRP = 32;             // roles padded (UMMA N)
 constexpr int kBoxCols = 32;        // 32 fp32 = 128 B = one swizzle row
-constexpr int kGroupCols = 128;     // columns per ring stage (UMMA M of P2)
+constexpr int kTileCols = 64;       // columns per P2 stage (UMMA M of P2)
 constexpr int kBoxBytes = kBlockRows * kBoxCols * 4;        // 8 KB
-constexpr int kStageBytes = 4 * kBoxBytes;                  // 32 KB
+constexpr int kStageABoxes = 4;                             // P1 stage: 128 columns
+constexpr int kStageABytes = kStageABoxes * kBoxBytes;      // 32 KB
+constexpr int kStageBytes = 2 * kBoxBytes;                  // 16 KB (P2 stage)
 constexpr int kHBoxBytes = kRP * kBoxCols * 4;              // 4 KB
 constexpr int kWnewBytes = kRP * kBlockRows * 4;            // 8 KB  (W_b^T, K-major: [role][row])
-constexpr int kMaxGroups = 6;                               // f <= 768
+constexpr int kMaxTiles = 12;                               // f <= 768
+constexpr int kMaxStagesA = 5, kMaxStagesB = 4;
+constexpr int kEpiStageFloats = 16 * 33;                    // per-warp W tile staging (padded)
 constexpr float kEps = 1.1920928955078125e-07f;
 
 // TMEM column map (512 columns allocated)
 constexpr int kColD1 = 0;      // 2 x 32: XHt double buffer (M=64 layout)
 constexpr int kColWtW = 64;    // 32: W^T W (M=64 layout, rows 0..31 valid)
-constexpr int kColD2 = 96;     // groups x 32: (W^T X)^T, M=128 layout
+constexpr int kColD2 = 96;     // tiles x 32: (W^T X)^T, M=64 layout per 64-column tile
 constexpr int kTmemCols = 512;
 
 struct TcParams {
     int64_t n;
     int f, r;
-    int groups;          // ceil(f / 128)
-    int stages;          // ring depth
+    int groups;          // ceil(f / 128): P1 stages per block (H holds 4 * groups boxes)
+    int tiles;           // ceil(f / 64): P2 stages per block
+    int ring_a;          // P1 ring depth in 32 KB stages
+    int ring_b;          // P2 ring depth in 16 KB stages
     int64_t n_blocks;    // ceil(n / 64)
     const float* hht;    // [r, r]
     float* W;            // [n, r]
     float* part_wtx;     // [grid, 32, f]
     float* part_wtw;     // [grid, 32, r]
+    unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
+    int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
+                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -93,6 +116,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+// L2 prefetch of a whole tensor box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(map), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -128,6 +156,16 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GR_TRACE(role, blk, ev)                                                             \
+    do {                                                                                    \
+        if (p.trace && blockIdx.x == 0 && (blk) < 64)                                       \
+            p.trace[((role) * 64 + (blk)) * 8 + (ev)] = gtime();                            \
+    } while (0)
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -150,34 +188,39 @@ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 constexpr uint32_t kIdescP1 = make_idesc(64, kRP, 0, 0);    // X K-major, H K-major
-constexpr uint32_t kIdescP2 = make_idesc(128, kRP, 1, 0);   // X^T MN-major, W_b^T K-major
+constexpr uint32_t kIdescP2 = make_idesc(64, kRP, 1, 0);    // X^T MN-major, W_b^T K-major
 constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 0, 0);   // W_b^T K-major both sides
 
 // ---- shared memory carve-up ---------------------------------------------------------------------
 struct SmemLayout {
-    uint32_t h;        // groups * 4 boxes of 4 KB
-    uint32_t ring;     // stages * 32 KB
-    uint32_t wnew;     // 2 x 8 KB + 4 KB readable pad (W^T W reads rows 32..63 of "A")
+    uint32_t h;        // 4 * groups boxes of 4 KB
+    uint32_t ring_a;   // P1 ring: stages of 32 KB
+    uint32_t ring_b;   // P2 ring: stages of 16 KB
+    uint32_t wnew;     // 8 KB W_b^T tile + 4 KB readable pad (W^T W reads rows 32..63 of "A")
     uint32_t hht;      // 32 x 32 fp32
+    uint32_t epi;      // 4 warps x 16 x 33 floats
     uint32_t bars;     // mbarriers
     uint32_t tmem_ptr;
     uint32_t total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int groups, int stages) {
+__host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ring_b) {
     SmemLayout L;
     uint32_t off = 0;
     L.h = off;      off += (uint32_t)groups * 4 * kHBoxBytes;
-    L.ring = off;   off += (uint32_t)stages * kStageBytes;
-    L.wnew = off;   off += 2 * kWnewBytes + 4096;
+    off = (off + 1023u) & ~1023u;
+    L.ring_a = off; off += (uint32_t)ring_a * kStageABytes;
+    L.ring_b = off; off += (uint32_t)ring_b * kStageBytes;
+    L.wnew = off;   off += kWnewBytes + 4096;
     L.hht = off;    off += kRP * kRP * 4;
+    L.epi = off;    off += 4 * kEpiStageFloats * 4;
     L.bars = off;   off += 64 * 8;
     L.tmem_ptr = off; off += 16;
     L.total = off;
     return L;
 }
 // barrier slots
-enum { B_FULL = 0, B_EMPTY = 8, B_HFULL = 16, B_D1FULL = 17, B_D1EMPTY = 19, B_WFULL = 21,
-       B_WEMPTY = 23, B_D2FULL = 25, B_COUNT = 26 };
+enum { B_FULL_A = 0, B_EMPTY_A = 8, B_FULL_B = 16, B_EMPTY_B = 20, B_HFULL = 24, B_D1FULL = 25,
+       B_D1EMPTY = 27, B_WFULL = 29, B_WEMPTY = 30, B_D2FULL = 31, B_COUNT = 32 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
@@ -187,29 +230,31 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     // 1024-byte alignment for the 128B swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemLayout L = smem_layout(p.groups, p.stages);
+    const SmemLayout L = smem_layout(p.groups, p.ring_a, p.ring_b);
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_h = s_base + L.h, s_ring = s_base + L.ring, s_wnew = s_base + L.wnew;
+    const uint32_t s_h = s_base + L.h, s_ra = s_base + L.ring_a, s_rb = s_base + L.ring_b;
+    const uint32_t s_wnew = s_base + L.wnew;
     const uint32_t s_bars = s_base + L.bars;
     float* hht_s = reinterpret_cast<float*>(smem + L.hht);
     volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
     auto bar = [&](int slot) { return s_bars + 8u * (uint32_t)slot; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = p.groups, S = p.stages;
+    const int G = p.groups, T = p.tiles, NA = p.ring_a, NB = p.ring_b;
     // blocks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int64_t nb = (p.n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(bar(B_FULL_A + s), 1); mbar_init(bar(B_EMPTY_A + s), 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(bar(B_FULL_B + s), 1); mbar_init(bar(B_EMPTY_B + s), 1); }
         mbar_init(bar(B_HFULL), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_D1FULL + i), 1);
             mbar_init(bar(B_D1EMPTY + i), 4);
-            mbar_init(bar(B_WFULL + i), 4);
-            mbar_init(bar(B_WEMPTY + i), 1);
         }
+        mbar_init(bar(B_WFULL), 4);
+        mbar_init(bar(B_WEMPTY), 1);
         mbar_init(bar(B_D2FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -217,8 +262,8 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         const int a = i / kRP, b = i % kRP;
         hht_s[i] = (a < p.r && b < p.r) ? p.hht[a * p.r + b] : 0.f;
     }
-    // W^T tiles start as zeros (padded roles / rows stay zero), the pad must be finite
-    for (int i = threadIdx.x; i < (2 * kWnewBytes + 4096) / 4; i += kThreads)
+    // the W^T tile starts as zeros (padded roles stay zero), the pad behind it must be finite
+    for (int i = threadIdx.x; i < (kWnewBytes + 4096) / 4; i += kThreads)
         reinterpret_cast<float*>(smem + L.wnew)[i] = 0.f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -232,89 +277,108 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     const uint32_t tmem = *tmem_ptr_s;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer, P1 stream (HBM): H once, then 128-column stages =========
         if (lane == 0) {
             mbar_expect_tx(bar(B_HFULL), (uint32_t)G * 4 * kHBoxBytes);
             for (int c = 0; c < G * 4; ++c)
                 tma_load_2d(s_h + c * kHBoxBytes, &map_h, c * kBoxCols, 0, bar(B_HFULL));
             uint32_t it = 0;
-            auto load_stage = [&](const CUtensorMap* map, int64_t blk, int g) {
-                const int st = it % S;
-                mbar_wait(bar(B_EMPTY + st), ((it / S) & 1) ^ 1);
-                mbar_expect_tx(bar(B_FULL + st), kStageBytes);
-                const int row = (int)(blk * kBlockRows);
-                for (int c = 0; c < 4; ++c)
-                    tma_load_2d(s_ring + st * kStageBytes + c * kBoxBytes, map,
-                                g * kGroupCols + c * kBoxCols, row, bar(B_FULL + st));
-                ++it;
-            };
-            for (int64_t i = 0; i <= nb; ++i) {
-                if (i < nb)
-                    for (int g = 0; g < G; ++g) load_stage(&map_x_k, blockIdx.x + i * gridDim.x, g);
-                if (i >= 1)
-                    for (int g = 0; g < G; ++g)
-                        load_stage(&map_x_mn, blockIdx.x + (i - 1) * gridDim.x, g);
+            for (int64_t i = 0; i < nb; ++i) {
+                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows);
+                GR_TRACE(0, i, 0);
+                for (int g = 0; g < G; ++g, ++it) {
+                    const int st = it % NA;
+                    mbar_wait(bar(B_EMPTY_A + st), ((it / NA) & 1) ^ 1);
+                    if (g < 4) GR_TRACE(0, i, 1 + g);
+                    mbar_expect_tx(bar(B_FULL_A + st), kStageABytes);
+                    for (int c = 0; c < kStageABoxes; ++c)
+                        tma_load_2d(s_ra + st * kStageABytes + c * kBoxBytes, &map_x_k,
+                                    (g * kStageABoxes + c) * kBoxCols, row, bar(B_FULL_A + st));
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ================= TMA producer, P2 stream (L2 re-reads, 32-byte-atom swizzle) ==========
+        if (lane == 0 && !(p.debug & 8)) {
+            uint32_t it = 0;
+            for (int64_t i = 0; i < nb; ++i) {
+                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows);
+                for (int t = 0; t < T; ++t, ++it) {
+                    const int st = it % NB;
+                    mbar_wait(bar(B_EMPTY_B + st), ((it / NB) & 1) ^ 1);
+                    if (t < 8) GR_TRACE(1, i, t);
+                    mbar_expect_tx(bar(B_FULL_B + st), kStageBytes);
+                    for (int c = 0; c < 2; ++c)
+                        tma_load_2d(s_rb + st * kStageBytes + c * kBoxBytes, &map_x_mn,
+                                    t * kTileCols + c * kBoxCols, row, bar(B_FULL_B + st));
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             mbar_wait(bar(B_HFULL), 0);
-            uint32_t it = 0;
+            uint32_t ita = 0, itb = 0;
             for (int64_t i = 0; i <= nb; ++i) {
-                if (i < nb) {
-                    // ---- P1(i): XHt into D1[i & 1]
-                    const int buf = (int)(i & 1);
-                    mbar_wait(bar(B_D1EMPTY + buf), (uint32_t)(((i >> 1) & 1) ^ 1));
+                const bool do_p1 = i < nb, do_p2 = i >= 1;
+                const int buf1 = (int)(i & 1);
+                const int64_t j = i - 1;
+                const uint32_t d1 = tmem + kColD1 + buf1 * kRP;
+                if (do_p1) {
+                    // ---- P1(i): X_b . H^T into D1, 128 columns (16 k-steps) per stage
+                    GR_TRACE(2, i, 0);
+                    mbar_wait(bar(B_D1EMPTY + buf1), (uint32_t)(((i >> 1) & 1) ^ 1));
                     tc_fence_after();
-                    const uint32_t d1 = tmem + kColD1 + buf * kRP;
-                    for (int g = 0; g < G; ++g) {
-                        const int st = it % S;
-                        mbar_wait(bar(B_FULL + st), (it / S) & 1);
+                    for (int g = 0; g < G; ++g, ++ita) {
+                        const int st = ita % NA;
+                        mbar_wait(bar(B_FULL_A + st), (ita / NA) & 1);
+                        if (g == 0) GR_TRACE(2, i, 1);
                         tc_fence_after();
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t a0 = s_ring + st * kStageBytes + c * kBoxBytes;
-                            const uint32_t b0 = s_h + (g * 4 + c) * kHBoxBytes;
+#pragma unroll
+                        for (int c = 0; c < kStageABoxes; ++c) {
+                            const uint32_t a0 = s_ra + st * kStageABytes + c * kBoxBytes;
+                            const uint32_t b0 = s_h + (g * kStageABoxes + c) * kHBoxBytes;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
+                                if (!(p.debug & 1))
                                 tc_mma_tf32(d1, make_desc(a0 + k * 32, 16, 1024, kLayoutSw128),
                                             make_desc(b0 + k * 32, 16, 1024, kLayoutSw128),
                                             kIdescP1, (g | c | k) != 0);
                         }
-                        tc_commit(bar(B_EMPTY + st));
-                        ++it;
+                        tc_commit(bar(B_EMPTY_A + st));
                     }
-                    tc_commit(bar(B_D1FULL + buf));
+                    tc_commit(bar(B_D1FULL + buf1));
+                    GR_TRACE(2, i, 2);
                 }
-                if (i >= 1) {
-                    // ---- P2(i-1): (W^T X)^T and W^T W with the updated W of block i-1
-                    const int64_t j = i - 1;
-                    const int buf = (int)(j & 1);
-                    mbar_wait(bar(B_WFULL + buf), (uint32_t)((j >> 1) & 1));
+                if (do_p2) {
+                    // ---- P2(i-1): (W^T X)^T and W^T W with the updated W of block i-1.  Issued
+                    // after P1(i), so the epilogue of block i-1 had all of P1(i) to finish.
+                    mbar_wait(bar(B_WFULL), (uint32_t)(j & 1));
+                    GR_TRACE(2, j, 3);
                     tc_fence_after();
-                    const uint32_t w0 = s_wnew + buf * kWnewBytes;
-                    for (int g = 0; g < G; ++g) {
-                        const int st = it % S;
-                        mbar_wait(bar(B_FULL + st), (it / S) & 1);
+                    for (int t = 0; t < T; ++t, ++itb) {
+                        const int st = itb % NB;
+                        if (!(p.debug & 8)) mbar_wait(bar(B_FULL_B + st), (itb / NB) & 1);
                         tc_fence_after();
-                        const uint32_t a0 = s_ring + st * kStageBytes;
+                        const uint32_t a0 = s_rb + st * kStageBytes;
 #pragma unroll
                         for (int k = 0; k < 8; ++k)   // k-step = 8 rows of the block
-                            tc_mma_tf32(tmem + kColD2 + g * kRP,
+                            if (!(p.debug & 10))
+                            tc_mma_tf32(tmem + kColD2 + t * kRP,
                                         make_desc(a0 + k * 1024, kBoxBytes, 512, kLayoutSw128Base32),
-                                        make_desc(w0 + (k >> 2) * 4096 + (k & 3) * 32, 16, 1024,
+                                        make_desc(s_wnew + (k >> 2) * 4096 + (k & 3) * 32, 16, 1024,
                                                   kLayoutSw128),
                                         kIdescP2, (j | k) != 0);
-                        tc_commit(bar(B_EMPTY + st));
-                        ++it;
+                        tc_commit(bar(B_EMPTY_B + st));
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint64_t d = make_desc(w0 + (k >> 2) * 4096 + (k & 3) * 32, 16, 1024,
-                                                     kLayoutSw128);
+                        const uint64_t d = make_desc(s_wnew + (k >> 2) * 4096 + (k & 3) * 32, 16,
+                                                     1024, kLayoutSw128);
                         tc_mma_tf32(tmem + kColWtW, d, d, kIdescWtW, (j | k) != 0);
                     }
-                    tc_commit(bar(B_WEMPTY + buf));
+                    tc_commit(bar(B_WEMPTY));
+                    GR_TRACE(2, j, 4);
                 }
             }
             tc_commit(bar(B_D2FULL));
@@ -324,27 +388,36 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         const int q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int r = p.r;
+        float* stg = reinterpret_cast<float*>(smem + L.epi) + q * kEpiStageFloats;   // [16][33]
+        unsigned char* wt = smem + L.wnew;
         for (int64_t i = 0; i < nb; ++i) {
             const int buf = (int)(i & 1);
-            const uint32_t par = (uint32_t)((i >> 1) & 1);
-            mbar_wait(bar(B_D1FULL + buf), par);
-            tc_fence_after();
-            float xht[32];
-            tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
-            tc_fence_before();
+            // M=64 accumulator layout: row 16q + l of the block lives in lane l < 16 of quarter q
+            const int64_t row0 = (blockIdx.x + i * gridDim.x) * kBlockRows + q * 16;
+            const int rows_valid = (int)max((int64_t)0, min((int64_t)16, p.n - row0));
+            const int n_el = rows_valid * r;                // floats of this warp's W tile
+            float* wtile = p.W + row0 * r;                  // contiguous [rows_valid, r]
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 0);
+            // ---- W tile -> staging (coalesced 16-byte loads; independent of the MMA)
+            for (int e = lane * 4; e < 16 * r; e += 128) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (e + 3 < n_el) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4*>(wtile + e));
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+                    for (int u = 0; u < 4; ++u) if (e + u < n_el) v[u] = __ldcs(wtile + e + u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) stg[((e + u) / r) * 33 + (e + u) % r] = v[u];
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
-
-            // M=64 accumulator layout: row 16q + l lives in lane l < 16 of quarter q
-            const int row_in_blk = q * 16 + lane;
-            const int64_t row = (blockIdx.x + i * gridDim.x) * kBlockRows + row_in_blk;
-            const bool valid = lane < 16 && row < p.n;
             float w[32], den[32];
 #pragma unroll
             for (int l = 0; l < 32; ++l) {
-                w[l] = (valid && l < r) ? __ldg(p.W + row * r + l) : 0.f;
+                w[l] = (lane < 16 && l < r) ? stg[lane * 33 + l] : 0.f;
                 den[l] = 0.f;
             }
+            if (!(p.debug & 4))
 #pragma unroll
             for (int l = 0; l < 32; ++l) {
                 const float wl = w[l];
@@ -357,37 +430,63 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     den[jj + 3] = fmaf(wl, hv.w, den[jj + 3]);
                 }
             }
-            // the MMA of block i-2 must be done with this W^T buffer
-            mbar_wait(bar(B_WEMPTY + buf), par ^ 1);
-            unsigned char* wt = smem + L.wnew + buf * kWnewBytes;
+            // ---- XHt from TMEM
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
+            mbar_wait(bar(B_D1FULL + buf), (uint32_t)((i >> 1) & 1));
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
+            tc_fence_after();
+            float xht[32];
+            tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
+            // ---- W_new: to staging (for the coalesced store) and, tf32-rounded and transposed,
+            // into the K-major SW128 tile P2 reads.  P2(i-1) must be done with that tile.
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
+            mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
+            const int k = q * 16 + lane;                    // row of the block = K index of P2
 #pragma unroll
             for (int l = 0; l < 32; ++l) {
-                float d = den[l] == 0.f ? kEps : den[l];
-                const float wn = (valid && l < r) ? w[l] * (xht[l] / d) : 0.f;
-                if (valid && l < r) p.W[row * r + l] = wn;
+                const float d = den[l] == 0.f ? kEps : den[l];
+                const float wn = (lane < rows_valid && l < r) ? w[l] * (xht[l] / d) : 0.f;
                 if (lane < 16) {
-                    // K-major SW128 tile [role l][row k]: atom k/32, 128 B per role row,
-                    // 16-byte chunk index XOR (l % 8)
-                    const int k = row_in_blk;
+                    if (l < r) stg[lane * 33 + l] = wn;
+                    // tile [role l][row k]: atom k/32, 128 B per role row, 16-byte chunk ^ (l % 8)
                     const uint32_t off = (uint32_t)(k >> 5) * 4096 + (uint32_t)l * 128 +
                                          ((((uint32_t)(k & 31) >> 2) ^ ((uint32_t)l & 7)) << 4) +
                                          ((uint32_t)k & 3) * 4;
                     *reinterpret_cast<float*>(wt + off) = to_tf32(wn);
                 }
             }
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 5);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_WFULL + buf));
+            if (lane == 0) mbar_arrive(bar(B_WFULL));
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
+            // ---- staging -> global (coalesced 16-byte stores)
+            for (int e = lane * 4; e < 16 * r; e += 128) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = stg[((e + u) / r) * 33 + (e + u) % r];
+                if (e + 3 < n_el) {
+                    __stcs(reinterpret_cast<float4*>(wtile + e), make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+                    for (int u = 0; u < 4; ++u) if (e + u < n_el) __stcs(wtile + e + u, v[u]);
+                }
+            }
+            __syncwarp();
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 7);
         }
 
         // ---- final: dump the TMEM accumulators as this CTA's partials
         mbar_wait(bar(B_D2FULL), 0);
         tc_fence_after();
         float v[32];
-        for (int g = 0; g < G; ++g) {
-            tc_ld_32x32(tmem + lane_base + kColD2 + g * kRP, v);
-            const int col = g * kGroupCols + q * 32 + lane;   // M=128 layout: lane = row of D
-            if (col < p.f)
+        for (int t = 0; t < T; ++t) {
+            tc_ld_32x32(tmem + lane_base + kColD2 + t * kRP, v);
+            const int col = t * kTileCols + q * 16 + lane;   // M=64 layout: row 16q + l in lane l
+            if (lane < 16 && col < p.f)
 #pragma unroll
                 for (int l = 0; l < 32; ++l)
                     if (l < r)
@@ -415,7 +514,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 // ---- host side ------------------------------------------------------------------------------------
 struct TcState {
     int grid = 0;
-    int stages = 0;
+    int ring_a = 0, ring_b = 0;
     size_t smem_bytes = 0;
     float* d_part_wtx = nullptr;
     float* d_part_wtw = nullptr;
@@ -444,7 +543,7 @@ EncodeTiledFn encode_fn() {
 
 int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
               uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows,
-              CUtensorMapSwizzle swizzle) {
+              CUtensorMapSwizzle swizzle, bool plain_f32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(GR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t dims[2] = {cols, rows};
@@ -455,7 +554,7 @@ int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
         const char* s = getenv("GR_NMF_TMA_TF32");
         return !(s && s[0] == '0');
     }();
-    const CUresult rc = fn(map, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+    const CUresult rc = fn(map, (round_tf32 && !plain_f32) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                            2, const_cast<float*>(base), dims, strides, box, elem,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
@@ -469,14 +568,14 @@ int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
 bool gr::nmf_tc_supported(const gr_nmf* h, const float* X, int64_t ldx) {
     if (getenv("GR_NMF_DISABLE_TC")) return false;
     return h->r <= kRP && h->f % 4 == 0 && ldx % 4 == 0 && aligned16(X) &&
-           ceil_div(h->f, kGroupCols) <= kMaxGroups && h->n < ((int64_t)1 << 31) &&
+           ceil_div(h->f, kTileCols) <= kMaxTiles && h->n < ((int64_t)1 << 31) &&
            encode_fn() != nullptr;
 }
 
 int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float* H,
                          cudaStream_t st) {
     TcState* s = static_cast<TcState*>(h->tc_state);
-    const int groups = ceil_div(h->f, kGroupCols);
+    const int groups = ceil_div(h->f, kStageABoxes * kBoxCols), tiles = ceil_div(h->f, kTileCols);
     if (!s) {
         s = new (std::nothrow) TcState();
         if (!s) return fail(GR_ERR_OUT_OF_MEMORY, "nmf tc state");
@@ -487,10 +586,20 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         s->grid = (int)std::min<int64_t>(sms, n_blocks);
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
-        for (s->stages = 8; s->stages >= 2; --s->stages)
-            if ((size_t)smem_layout(groups, s->stages).total + 1024 <= (size_t)max_smem) break;
-        if (s->stages < 2) return fail(GR_ERR_CUDA, "nmf tc: shared memory budget too small");
-        s->smem_bytes = (size_t)smem_layout(groups, s->stages).total + 1024;
+        // shared memory left after H goes to the rings: the P1 (HBM) ring first -- three 32 KB
+        // stages stream at > 6.5 TB/s (tools/exp_tma.cu) -- then the P2 (L2) ring
+        auto fits = [&](int a, int b) {
+            return (size_t)smem_layout(groups, a, b).total + 1024 <= (size_t)max_smem;
+        };
+        s->ring_a = 3;
+        s->ring_b = 2;
+        if (!fits(s->ring_a, s->ring_b)) s->ring_a = 2;
+        if (!fits(s->ring_a, s->ring_b)) return fail(GR_ERR_CUDA, "nmf tc: shared memory budget");
+        while (s->ring_b < kMaxStagesB && fits(s->ring_a, s->ring_b + 1)) ++s->ring_b;
+        while (s->ring_a < kMaxStagesA && fits(s->ring_a + 1, s->ring_b)) ++s->ring_a;
+        if (const char* e = getenv("GR_NMF_RING_A")) s->ring_a = std::max(1, std::min(s->ring_a, atoi(e)));
+        if (const char* e = getenv("GR_NMF_RING_B")) s->ring_b = std::max(1, std::min(s->ring_b, atoi(e)));
+        s->smem_bytes = (size_t)smem_layout(groups, s->ring_a, s->ring_b).total + 1024;
         GR_CUDA_TRY(cudaFuncSetAttribute(nmf_fused_tc_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)s->smem_bytes));
@@ -520,18 +629,47 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     p.f = h->f;
     p.r = h->r;
     p.groups = groups;
-    p.stages = s->stages;
+    p.tiles = tiles;
+    p.ring_a = s->ring_a;
+    p.ring_b = s->ring_b;
     p.n_blocks = ceil_div<int64_t>(h->n, kBlockRows);
     p.hht = h->d_hht;
     p.W = W;
     p.part_wtx = s->d_part_wtx;
     p.part_wtw = s->d_part_wtw;
+    p.trace = nullptr;
+    static unsigned long long* d_trace = nullptr;
+    if (getenv("GR_NMF_TRACE")) {
+        if (!d_trace) cudaMalloc(&d_trace, 4 * 64 * 8 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(unsigned long long), st);
+        p.trace = d_trace;
+    }
+    p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
     nmf_fused_tc_kernel<<<s->grid, kThreads, s->smem_bytes, st>>>(s->map_x_k, s->map_x_mn,
                                                                  s->map_h, p);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return fail(GR_ERR_CUDA, "nmf_fused_tc_kernel launch failed: %s", cudaGetErrorString(e));
+    if (p.trace) {
+        static unsigned long long h_trace[4 * 64 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h_trace, d_trace, sizeof(h_trace), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (auto v : h_trace) if (v && v < t0) t0 = v;
+        const char* names[4] = {"prodA", "prodB", "mma", "epi0"};
+        const int first = getenv("GR_NMF_TRACE_FIRST") ? atoi(getenv("GR_NMF_TRACE_FIRST")) : 8;
+        for (int b = first; b < first + 6; ++b)
+            for (int role = 0; role < 4; ++role) {
+                printf("blk %2d %-5s", b, names[role]);
+                for (int ev = 0; ev < 8; ++ev) {
+                    const unsigned long long v = h_trace[(role * 64 + b) * 8 + ev];
+                    if (v) printf(" %8.2f", (double)(v - t0) / 1000.0); else printf("        -");
+                }
+                printf("\n");
+            }
+        fflush(stdout);
+    }
     return nmf_finish_iteration(h, s->d_part_wtx, s->d_part_wtw, s->grid, kRP, H, st);
 }
 

@@ -43,13 +43,61 @@ def get_nmf_decomposition(X: np.ndarray, n_roles: int) -> FactorTuple:
     return W.double().cpu().numpy(), H.double().cpu().numpy()
 
 
+class NmfSolver:
+    """A gr_nmf_t handle (workspaces, tensor maps) that can be reused across calls on matrices
+    of the same shape -- `update` runs multiplicative updates IN PLACE on W and H."""
+
+    def __init__(self, n: int, f: int, r: int, device=None):
+        self.n, self.f, self.r = int(n), int(f), int(r)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self._lib = _native.load()
+        self._handle = c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.gr_nmf_create(byref(self._handle), self.n, self.f, self.r,
+                                                  self.device.index or 0), 'gr_nmf_create')
+        self.last_path = None
+
+    def update(self, X, W, H, max_iter=MAX_ITER, tol=TOL, check_every=CHECK_EVERY,
+               use_tf32=True, want_error=True, stream=None) -> Tuple[int, float]:
+        """Returns (n_iter, error); error is NaN when tol == 0 and want_error is False (no
+        extra pass over X is made then)."""
+        for name, t, shape in (('X', X, (self.n, self.f)), ('W', W, (self.n, self.r)),
+                               ('H', H, (self.r, self.f))):
+            if not (t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == shape):
+                raise ValueError(f'{name} must be a float32 CUDA tensor of shape {shape}')
+        if X.stride(1) != 1 or not W.is_contiguous() or not H.is_contiguous():
+            raise ValueError('X needs unit column stride; W and H must be contiguous')
+        n_iter, err = c_int32(0), c_double(float('nan'))
+        err_ptr = byref(err) if (want_error or tol > 0) else None
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.gr_nmf_mu_f32(
+                self._handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
+                c_void_p(H.data_ptr()), max_iter, float(tol), check_every,
+                1 if use_tf32 else 0, byref(n_iter), err_ptr, _native._stream_ptr(stream)),
+                'gr_nmf_mu_f32')
+        self.last_path = 'tcgen05' if self._lib.gr_nmf_last_path(self._handle) else 'ffma'
+        return int(n_iter.value), float(err.value)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            self._lib.gr_nmf_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def nmf_mu(X: torch.Tensor, W0: torch.Tensor, H0: torch.Tensor, max_iter: int = MAX_ITER,
            tol: float = TOL, check_every: int = CHECK_EVERY, use_tf32: bool = True,
            stream=None) -> Tuple[torch.Tensor, torch.Tensor, int, float]:
     """Multiplicative-update NMF from an explicit start (sklearn's init='custom').
 
     X [n, f], W0 [n, r], H0 [r, f]: float32 CUDA tensors.  Returns (W, H, n_iter, error) with
-    error = ||X - W H||_F at the last convergence check.
+    error = ||X - W H||_F at the last convergence check (at the end when tol == 0).
     """
     for name, t in (('X', X), ('W0', W0), ('H0', H0)):
         if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
@@ -60,25 +108,16 @@ def nmf_mu(X: torch.Tensor, W0: torch.Tensor, H0: torch.Tensor, max_iter: int = 
         raise ValueError('shapes must be X [n, f], W0 [n, r], H0 [r, f]')
     if X.stride(1) != 1:
         X = X.contiguous()
-    lib = _native.load()
     W = W0.clone().contiguous()
     H = H0.clone().contiguous()
-    handle = c_void_p()
-    with torch.cuda.device(X.device):
-        _native.check(lib.gr_nmf_create(byref(handle), n, f, r, X.device.index or 0),
-                      'gr_nmf_create')
-        try:
-            n_iter, err = c_int32(0), c_double(0.0)
-            _native.check(lib.gr_nmf_mu_f32(
-                handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
-                c_void_p(H.data_ptr()), max_iter, float(tol), check_every,
-                1 if use_tf32 else 0, byref(n_iter), byref(err), _native._stream_ptr(stream)),
-                'gr_nmf_mu_f32')
-            global last_path
-            last_path = 'tcgen05' if lib.gr_nmf_last_path(handle) else 'ffma'
-        finally:
-            lib.gr_nmf_destroy(handle)
-    return W, H, int(n_iter.value), float(err.value)
+    solver = NmfSolver(n, f, r, X.device)
+    try:
+        n_iter, err = solver.update(X, W, H, max_iter, tol, check_every, use_tf32, True, stream)
+        global last_path
+        last_path = solver.last_path
+    finally:
+        solver.close()
+    return W, H, n_iter, err
 
 
 def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor) -> float:
