@@ -4,8 +4,10 @@
 //
 // Per 64-row block b of X (persistent CTAs, one per SM, blocks round-robin):
 //   P1  XHt[64, 32]      = X_b (64 x f, K-major)  .  H^T      tcgen05.mma M=64  N=32 K=8 x f/8
-//   E   W_b             *= XHt / (W_b (H H^T))               epilogue warps: tcgen05.ld, fp32 math,
-//                                                            W_b -> global, tf32(W_b)^T -> smem
+//   P1' Den[64, 32]      = W_b (64 x 32, K-major)  .  (H H^T)  tcgen05.mma M=64  N=32 K=8 x 4
+//   E   W_b             *= XHt / Den                         epilogue warps: tcgen05.ld, 32 fp32
+//                                                            ops per row; W_b tiles move by TMA
+//                                                            (load + store), tf32(W_b) -> smem
 //   P2  (W^T X)^T[f, 32] += X_b^T (MN-major)     .  W_b      tcgen05.mma M=64  N=32 K=8 x 8 per
 //                                                            64 columns; accumulators stay in TMEM
 //       (W^T W)[32, 32]  += W_b^T                 .  W_b      tcgen05.mma M=64  N=32 K=8 x 8
@@ -31,9 +33,10 @@
 //   * per-box (8 KB) mbarrier stages: a single-thread producer/consumer handshake costs ~500
 //     cycles, which caps a stream at ~4.4 TB/s regardless of ring depth; 32 KB per barrier
 //     streams at 6.6-7.4 TB/s with only 3 stages (tools/exp_tma.cu);
-//   * scalar per-row W loads/stores in the epilogue (16 rows x 4 B per warp instruction) cost
-//     ~5 us per block; the W tile of a warp is contiguous in memory, so it is staged through
-//     shared memory with coalesced 16-byte accesses instead.
+//   * an epilogue that computes W (H H^T) per row on CUDA cores (1024 FMA + 32 IEEE divisions
+//     per thread, one warp per scheduler) takes ~10 us per block and bounds the kernel
+//     (timeline trace, GR_NMF_TRACE); the r x r product therefore also runs on the tensor
+//     core (P1'), W tiles are moved by TMA, and the epilogue is ~250 instructions per row.
 
 #include <cuda.h>
 
@@ -58,15 +61,16 @@ constexpr int kStageABytes = kStageABoxes * kBoxBytes;      // 32 KB
 constexpr int kStageBytes = 2 * kBoxBytes;                  // 16 KB (P2 stage)
 constexpr int kHBoxBytes = kRP * kBoxCols * 4;              // 4 KB
 constexpr int kWnewBytes = kRP * kBlockRows * 4;            // 8 KB  (W_b^T, K-major: [role][row])
-constexpr int kMaxTiles = 12;                               // f <= 768
+constexpr int kMaxTiles = 11;                               // f <= 704 (TMEM columns)
+constexpr int kWSubBytes = 16 * kRP * 4;                    // 2 KB: one warp's 16 rows of a W tile
 constexpr int kMaxStagesA = 5, kMaxStagesB = 4;
-constexpr int kEpiStageFloats = 16 * 33;                    // per-warp W tile staging (padded)
 constexpr float kEps = 1.1920928955078125e-07f;
 
 // TMEM column map (512 columns allocated)
 constexpr int kColD1 = 0;      // 2 x 32: XHt double buffer (M=64 layout)
-constexpr int kColWtW = 64;    // 32: W^T W (M=64 layout, rows 0..31 valid)
-constexpr int kColD2 = 96;     // tiles x 32: (W^T X)^T, M=64 layout per 64-column tile
+constexpr int kColDen = 64;    // 2 x 32: W (H H^T) double buffer (M=64 layout)
+constexpr int kColWtW = 128;   // 32: W^T W (M=64 layout, rows 0..31 valid, 32..63 duplicates)
+constexpr int kColD2 = 160;    // tiles x 32: (W^T X)^T, M=64 layout per 64-column tile
 constexpr int kTmemCols = 512;
 
 struct TcParams {
@@ -77,8 +81,6 @@ struct TcParams {
     int ring_a;          // P1 ring depth in 32 KB stages
     int ring_b;          // P2 ring depth in 16 KB stages
     int64_t n_blocks;    // ceil(n / 64)
-    const float* hht;    // [r, r]
-    float* W;            // [n, r]
     float* part_wtx;     // [grid, 32, f]
     float* part_wtw;     // [grid, 32, r]
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
@@ -110,12 +112,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y,
                                             uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 // L2 prefetch of a whole tensor box (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
@@ -188,17 +207,17 @@ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 constexpr uint32_t kIdescP1 = make_idesc(64, kRP, 0, 0);    // X K-major, H K-major
-constexpr uint32_t kIdescP2 = make_idesc(64, kRP, 1, 0);    // X^T MN-major, W_b^T K-major
-constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 0, 0);   // W_b^T K-major both sides
+constexpr uint32_t kIdescP2 = make_idesc(64, kRP, 1, 1);    // X^T MN-major, W_b MN-major
+constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 1, 1);   // W_b MN-major on both sides
 
 // ---- shared memory carve-up ---------------------------------------------------------------------
 struct SmemLayout {
     uint32_t h;        // 4 * groups boxes of 4 KB
     uint32_t ring_a;   // P1 ring: stages of 32 KB
     uint32_t ring_b;   // P2 ring: stages of 16 KB
-    uint32_t wnew;     // 8 KB W_b^T tile + 4 KB readable pad (W^T W reads rows 32..63 of "A")
-    uint32_t hht;      // 32 x 32 fp32
-    uint32_t epi;      // 4 warps x 16 x 33 floats
+    uint32_t wio;      // 2 x 8 KB: W_b tile in (TMA load, fp32, K-major SW128) / out (TMA store)
+    uint32_t wnew;     // 8 KB: tf32(W_b new), [row][role] in the 32-byte-atom 128B swizzle
+    uint32_t hht;      // 4 KB: H H^T as a K-major SW128 tile (TMA)
     uint32_t bars;     // mbarriers
     uint32_t tmem_ptr;
     uint32_t total;
@@ -206,13 +225,13 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ring_b) {
     SmemLayout L;
     uint32_t off = 0;
-    L.h = off;      off += (uint32_t)groups * 4 * kHBoxBytes;
+    L.h = off;      off += (uint32_t)groups * kStageABoxes * kHBoxBytes;
     off = (off + 1023u) & ~1023u;
     L.ring_a = off; off += (uint32_t)ring_a * kStageABytes;
     L.ring_b = off; off += (uint32_t)ring_b * kStageBytes;
-    L.wnew = off;   off += kWnewBytes + 4096;
-    L.hht = off;    off += kRP * kRP * 4;
-    L.epi = off;    off += 4 * kEpiStageFloats * 4;
+    L.wio = off;    off += 2 * kWnewBytes;
+    L.wnew = off;   off += kWnewBytes;
+    L.hht = off;    off += kHBoxBytes;
     L.bars = off;   off += 64 * 8;
     L.tmem_ptr = off; off += 16;
     L.total = off;
@@ -220,12 +239,14 @@ __host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ri
 }
 // barrier slots
 enum { B_FULL_A = 0, B_EMPTY_A = 8, B_FULL_B = 16, B_EMPTY_B = 20, B_HFULL = 24, B_D1FULL = 25,
-       B_D1EMPTY = 27, B_WFULL = 29, B_WEMPTY = 30, B_D2FULL = 31, B_COUNT = 32 };
+       B_D1EMPTY = 27, B_WFULL = 29, B_WEMPTY = 30, B_D2FULL = 31, B_WINFULL = 32, B_COUNT = 34 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     const __grid_constant__ CUtensorMap map_x_mn,
-                    const __grid_constant__ CUtensorMap map_h, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_h,
+                    const __grid_constant__ CUtensorMap map_hht,
+                    const __grid_constant__ CUtensorMap map_w, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -233,9 +254,8 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     const SmemLayout L = smem_layout(p.groups, p.ring_a, p.ring_b);
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_h = s_base + L.h, s_ra = s_base + L.ring_a, s_rb = s_base + L.ring_b;
-    const uint32_t s_wnew = s_base + L.wnew;
+    const uint32_t s_wnew = s_base + L.wnew, s_wio = s_base + L.wio, s_hht = s_base + L.hht;
     const uint32_t s_bars = s_base + L.bars;
-    float* hht_s = reinterpret_cast<float*>(smem + L.hht);
     volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
     auto bar = [&](int slot) { return s_bars + 8u * (uint32_t)slot; };
 
@@ -256,21 +276,15 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         mbar_init(bar(B_WFULL), 4);
         mbar_init(bar(B_WEMPTY), 1);
         mbar_init(bar(B_D2FULL), 1);
+        mbar_init(bar(B_WINFULL), 4);
+        mbar_init(bar(B_WINFULL + 1), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < kRP * kRP; i += kThreads) {
-        const int a = i / kRP, b = i % kRP;
-        hht_s[i] = (a < p.r && b < p.r) ? p.hht[a * p.r + b] : 0.f;
-    }
-    // the W^T tile starts as zeros (padded roles stay zero), the pad behind it must be finite
-    for (int i = threadIdx.x; i < (kWnewBytes + 4096) / 4; i += kThreads)
-        reinterpret_cast<float*>(smem + L.wnew)[i] = 0.f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void*)tmem_ptr_s)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zero-fill visible to UMMA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -279,9 +293,10 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     if (warp == 0) {
         // ================= TMA producer, P1 stream (HBM): H once, then 128-column stages =========
         if (lane == 0) {
-            mbar_expect_tx(bar(B_HFULL), (uint32_t)G * 4 * kHBoxBytes);
-            for (int c = 0; c < G * 4; ++c)
+            mbar_expect_tx(bar(B_HFULL), (uint32_t)(G * kStageABoxes + 1) * kHBoxBytes);
+            for (int c = 0; c < G * kStageABoxes; ++c)
                 tma_load_2d(s_h + c * kHBoxBytes, &map_h, c * kBoxCols, 0, bar(B_HFULL));
+            tma_load_2d(s_hht, &map_hht, 0, 0, bar(B_HFULL));
             uint32_t it = 0;
             for (int64_t i = 0; i < nb; ++i) {
                 const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows);
@@ -289,7 +304,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                 for (int g = 0; g < G; ++g, ++it) {
                     const int st = it % NA;
                     mbar_wait(bar(B_EMPTY_A + st), ((it / NA) & 1) ^ 1);
-                    if (g < 4) GR_TRACE(0, i, 1 + g);
+                    if (g < 7) GR_TRACE(0, i, 1 + g);
                     mbar_expect_tx(bar(B_FULL_A + st), kStageABytes);
                     for (int c = 0; c < kStageABoxes; ++c)
                         tma_load_2d(s_ra + st * kStageABytes + c * kBoxBytes, &map_x_k,
@@ -318,6 +333,11 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         // ================= MMA issuer =================
         if (lane == 0) {
             mbar_wait(bar(B_HFULL), 0);
+            // Issue order: P1(0); then P1(i), P2(i-1) for i >= 1; finally P2(last).  Measured
+            // alternatives (C5, r = 32): interleaving P2(i-1) stages into P1(i) 9.6 ms, polling
+            // both rings and consuming whichever stage landed 9.6 - 9.9 ms, this order 8.4 ms --
+            // with 128 KB of ring space the slot turn-around bounds both streams, and blocking
+            // mbarrier waits have less latency than a polling loop.
             uint32_t ita = 0, itb = 0;
             for (int64_t i = 0; i <= nb; ++i) {
                 const bool do_p1 = i < nb, do_p2 = i >= 1;
@@ -347,12 +367,21 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                         }
                         tc_commit(bar(B_EMPTY_A + st));
                     }
+                    // ---- P1'(i): Den = W_b . (H H^T) from the TMA-loaded W tile.  (Its load was
+                    // issued after the epilogue of block i-2, which needed P2(i-3): already done.)
+                    mbar_wait(bar(B_WINFULL + buf1), (uint32_t)((i >> 1) & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_tf32(tmem + kColDen + buf1 * kRP,
+                                    make_desc(s_wio + buf1 * kWnewBytes + k * 32, 16, 1024, kLayoutSw128),
+                                    make_desc(s_hht + k * 32, 16, 1024, kLayoutSw128), kIdescP1,
+                                    k != 0);
                     tc_commit(bar(B_D1FULL + buf1));
                     GR_TRACE(2, i, 2);
                 }
                 if (do_p2) {
-                    // ---- P2(i-1): (W^T X)^T and W^T W with the updated W of block i-1.  Issued
-                    // after P1(i), so the epilogue of block i-1 had all of P1(i) to finish.
+                    // ---- P2(i-1): (W^T X)^T and W^T W with the updated W of block i-1
                     mbar_wait(bar(B_WFULL), (uint32_t)(j & 1));
                     GR_TRACE(2, j, 3);
                     tc_fence_after();
@@ -366,15 +395,15 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                             if (!(p.debug & 10))
                             tc_mma_tf32(tmem + kColD2 + t * kRP,
                                         make_desc(a0 + k * 1024, kBoxBytes, 512, kLayoutSw128Base32),
-                                        make_desc(s_wnew + (k >> 2) * 4096 + (k & 3) * 32, 16, 1024,
-                                                  kLayoutSw128),
+                                        make_desc(s_wnew + k * 1024, 0, 512, kLayoutSw128Base32),
                                         kIdescP2, (j | k) != 0);
                         tc_commit(bar(B_EMPTY_B + st));
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint64_t d = make_desc(s_wnew + (k >> 2) * 4096 + (k & 3) * 32, 16,
-                                                     1024, kLayoutSw128);
+                        // LBO = 0: the second 32-role group of "A" aliases the first (rows 32..63 of
+                        // the accumulator duplicate rows 0..31 and are never read)
+                        const uint64_t d = make_desc(s_wnew + k * 1024, 0, 512, kLayoutSw128Base32);
                         tc_mma_tf32(tmem + kColWtW, d, d, kIdescWtW, (j | k) != 0);
                     }
                     tc_commit(bar(B_WEMPTY));
@@ -388,96 +417,82 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         const int q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int r = p.r;
-        float* stg = reinterpret_cast<float*>(smem + L.epi) + q * kEpiStageFloats;   // [16][33]
-        unsigned char* wt = smem + L.wnew;
+        // this warp's 16 rows of the W tile: rows 16q..16q+15 = two 1 KB swizzle atoms
+        auto w_sub = [&](int buf) { return s_wio + buf * kWnewBytes + q * kWSubBytes; };
+        auto load_w_sub = [&](int64_t i) {   // elected lane: TMA load of block i's sub-tile
+            if (i >= nb) return;
+            const int buf = (int)(i & 1);
+            const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows) + q * 16;
+            mbar_expect_tx(bar(B_WINFULL + buf), kWSubBytes);
+            tma_load_2d(w_sub(buf), &map_w, 0, row, bar(B_WINFULL + buf));
+        };
+        if (lane == 0) { load_w_sub(0); load_w_sub(1); }
+        const int k = q * 16 + (lane & 15);              // row of the block held by this lane
         for (int64_t i = 0; i < nb; ++i) {
             const int buf = (int)(i & 1);
-            // M=64 accumulator layout: row 16q + l of the block lives in lane l < 16 of quarter q
-            const int64_t row0 = (blockIdx.x + i * gridDim.x) * kBlockRows + q * 16;
-            const int rows_valid = (int)max((int64_t)0, min((int64_t)16, p.n - row0));
-            const int n_el = rows_valid * r;                // floats of this warp's W tile
-            float* wtile = p.W + row0 * r;                  // contiguous [rows_valid, r]
+            const uint32_t par = (uint32_t)((i >> 1) & 1);
             if (q == 0 && lane == 0) GR_TRACE(3, i, 0);
-            // ---- W tile -> staging (coalesced 16-byte loads; independent of the MMA)
-            for (int e = lane * 4; e < 16 * r; e += 128) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (e + 3 < n_el) {
-                    const float4 t = __ldcs(reinterpret_cast<const float4*>(wtile + e));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                } else {
-                    for (int u = 0; u < 4; ++u) if (e + u < n_el) v[u] = __ldcs(wtile + e + u);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) stg[((e + u) / r) * 33 + (e + u) % r] = v[u];
-            }
-            __syncwarp();
-            float w[32], den[32];
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                w[l] = (lane < 16 && l < r) ? stg[lane * 33 + l] : 0.f;
-                den[l] = 0.f;
-            }
-            if (!(p.debug & 4))
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const float wl = w[l];
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hht_s + l * kRP + jj);
-                    den[jj] = fmaf(wl, hv.x, den[jj]);
-                    den[jj + 1] = fmaf(wl, hv.y, den[jj + 1]);
-                    den[jj + 2] = fmaf(wl, hv.z, den[jj + 2]);
-                    den[jj + 3] = fmaf(wl, hv.w, den[jj + 3]);
-                }
-            }
-            // ---- XHt from TMEM
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
-            mbar_wait(bar(B_D1FULL + buf), (uint32_t)((i >> 1) & 1));
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
+            // ---- XHt and Den from TMEM (M=64 layout: row 16q + l in lane l < 16 of quarter q)
+            mbar_wait(bar(B_D1FULL + buf), par);
+            mbar_wait(bar(B_WINFULL + buf), par);        // the W tile the MMA already consumed
             tc_fence_after();
-            float xht[32];
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
+            float xht[32], den[32];
             tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
+            tc_ld_32x32(tmem + lane_base + kColDen + buf * kRP, den);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
-            // ---- W_new: to staging (for the coalesced store) and, tf32-rounded and transposed,
-            // into the K-major SW128 tile P2 reads.  P2(i-1) must be done with that tile.
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
+            // ---- W row from the tile: [row][role], 16-byte chunk c at c ^ (row % 8)
+            unsigned char* wrow = smem + L.wio + buf * kWnewBytes + (uint32_t)k * 128;
+            float wn[32];
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 t = *reinterpret_cast<const float4*>(wrow + ((c ^ (k & 7)) << 4));
+                    wn[4 * c] = t.x; wn[4 * c + 1] = t.y; wn[4 * c + 2] = t.z; wn[4 * c + 3] = t.w;
+                }
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const float d = den[l] == 0.f ? kEps : den[l];
+                    wn[l] = l < r ? wn[l] * __fdividef(xht[l], d) : 0.f;
+                }
+                // fp32 result back into the tile (TMA store source)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(wrow + ((c ^ (k & 7)) << 4)) =
+                        make_float4(wn[4 * c], wn[4 * c + 1], wn[4 * c + 2], wn[4 * c + 3]);
+            }
             if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
+            // ---- tf32 copy for P2 / W^T W: [row][role], 32-byte chunk c at c ^ (row % 4).
+            // P2(i-1) must be done with that tile.
             mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));
             if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
-            const int k = q * 16 + lane;                    // row of the block = K index of P2
+            if (lane < 16) {
+                unsigned char* trow = smem + L.wnew + (uint32_t)k * 128;
 #pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const float d = den[l] == 0.f ? kEps : den[l];
-                const float wn = (lane < rows_valid && l < r) ? w[l] * (xht[l] / d) : 0.f;
-                if (lane < 16) {
-                    if (l < r) stg[lane * 33 + l] = wn;
-                    // tile [role l][row k]: atom k/32, 128 B per role row, 16-byte chunk ^ (l % 8)
-                    const uint32_t off = (uint32_t)(k >> 5) * 4096 + (uint32_t)l * 128 +
-                                         ((((uint32_t)(k & 31) >> 2) ^ ((uint32_t)l & 7)) << 4) +
-                                         ((uint32_t)k & 3) * 4;
-                    *reinterpret_cast<float*>(wt + off) = to_tf32(wn);
-                }
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(trow + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4))) =
+                        make_float4(to_tf32(wn[4 * c]), to_tf32(wn[4 * c + 1]),
+                                    to_tf32(wn[4 * c + 2]), to_tf32(wn[4 * c + 3]));
             }
             if (q == 0 && lane == 0) GR_TRACE(3, i, 5);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_WFULL));
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
-            // ---- staging -> global (coalesced 16-byte stores)
-            for (int e = lane * 4; e < 16 * r; e += 128) {
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = stg[((e + u) / r) * 33 + (e + u) % r];
-                if (e + 3 < n_el) {
-                    __stcs(reinterpret_cast<float4*>(wtile + e), make_float4(v[0], v[1], v[2], v[3]));
-                } else {
-                    for (int u = 0; u < 4; ++u) if (e + u < n_el) __stcs(wtile + e + u, v[u]);
-                }
+            if (lane == 0) {
+                mbar_arrive(bar(B_WFULL));
+                // ---- W tile out (rows beyond n / roles beyond r are clipped by the tensor map),
+                // then reuse the buffer for block i + 2
+                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows) + q * 16;
+                tma_store_2d(&map_w, 0, row, w_sub(buf));
+                tma_store_commit_and_wait_read();
+                load_w_sub(i + 2);
             }
             __syncwarp();
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 7);
+            if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
         // ---- final: dump the TMEM accumulators as this CTA's partials
         mbar_wait(bar(B_D2FULL), 0);
@@ -518,7 +533,8 @@ struct TcState {
     size_t smem_bytes = 0;
     float* d_part_wtx = nullptr;
     float* d_part_wtw = nullptr;
-    CUtensorMap map_x_k, map_x_mn, map_h;
+    CUtensorMap map_x_k, map_x_mn, map_h, map_hht, map_w;
+    const float* W = nullptr;
     const float* X = nullptr;   // what the X maps were encoded for
     int64_t ldx = 0;
     const float* H = nullptr;
@@ -567,7 +583,7 @@ int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
 
 bool gr::nmf_tc_supported(const gr_nmf* h, const float* X, int64_t ldx) {
     if (getenv("GR_NMF_DISABLE_TC")) return false;
-    return h->r <= kRP && h->f % 4 == 0 && ldx % 4 == 0 && aligned16(X) &&
+    return h->r <= kRP && h->r % 4 == 0 && h->f % 4 == 0 && ldx % 4 == 0 && aligned16(X) &&
            ceil_div(h->f, kTileCols) <= kMaxTiles && h->n < ((int64_t)1 << 31) &&
            encode_fn() != nullptr;
 }
@@ -591,14 +607,19 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         auto fits = [&](int a, int b) {
             return (size_t)smem_layout(groups, a, b).total + 1024 <= (size_t)max_smem;
         };
+        // P1 (HBM) ring: three 32 KB stages; P2 (L2) ring: two 16 KB stages; anything left goes
+        // to the P2 ring first (its slots turn around faster)
         s->ring_a = 3;
         s->ring_b = 2;
         if (!fits(s->ring_a, s->ring_b)) s->ring_a = 2;
         if (!fits(s->ring_a, s->ring_b)) return fail(GR_ERR_CUDA, "nmf tc: shared memory budget");
         while (s->ring_b < kMaxStagesB && fits(s->ring_a, s->ring_b + 1)) ++s->ring_b;
         while (s->ring_a < kMaxStagesA && fits(s->ring_a + 1, s->ring_b)) ++s->ring_a;
-        if (const char* e = getenv("GR_NMF_RING_A")) s->ring_a = std::max(1, std::min(s->ring_a, atoi(e)));
-        if (const char* e = getenv("GR_NMF_RING_B")) s->ring_b = std::max(1, std::min(s->ring_b, atoi(e)));
+        if (getenv("GR_NMF_RING_A") && getenv("GR_NMF_RING_B") &&
+            fits(atoi(getenv("GR_NMF_RING_A")), atoi(getenv("GR_NMF_RING_B")))) {
+            s->ring_a = std::max(1, std::min(kMaxStagesA, atoi(getenv("GR_NMF_RING_A"))));
+            s->ring_b = std::max(1, std::min(kMaxStagesB, atoi(getenv("GR_NMF_RING_B"))));
+        }
         s->smem_bytes = (size_t)smem_layout(groups, s->ring_a, s->ring_b).total + 1024;
         GR_CUDA_TRY(cudaFuncSetAttribute(nmf_fused_tc_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -620,7 +641,17 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         if (int rc = encode_2d(&s->map_h, H, (uint64_t)h->f, (uint64_t)h->r, (uint64_t)h->f * 4,
                                kBoxCols, kRP, CU_TENSOR_MAP_SWIZZLE_128B))
             return rc;
+        if (int rc = encode_2d(&s->map_hht, h->d_hht, (uint64_t)h->r, (uint64_t)h->r,
+                               (uint64_t)h->r * 4, kRP, kRP, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
         s->H = H;
+    }
+    if (s->W != W) {
+        // fp32 (no tf32 rounding: the tile is also the TMA store source), 16 rows per box
+        if (int rc = encode_2d(&s->map_w, W, (uint64_t)h->r, (uint64_t)h->n, (uint64_t)h->r * 4,
+                               kRP, 16, CU_TENSOR_MAP_SWIZZLE_128B, true))
+            return rc;
+        s->W = W;
     }
 
     if (int rc = nmf_hht(h, H, st)) return rc;
@@ -633,8 +664,6 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     p.ring_a = s->ring_a;
     p.ring_b = s->ring_b;
     p.n_blocks = ceil_div<int64_t>(h->n, kBlockRows);
-    p.hht = h->d_hht;
-    p.W = W;
     p.part_wtx = s->d_part_wtx;
     p.part_wtw = s->d_part_wtw;
     p.trace = nullptr;
@@ -645,8 +674,8 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         p.trace = d_trace;
     }
     p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
-    nmf_fused_tc_kernel<<<s->grid, kThreads, s->smem_bytes, st>>>(s->map_x_k, s->map_x_mn,
-                                                                 s->map_h, p);
+    nmf_fused_tc_kernel<<<s->grid, kThreads, s->smem_bytes, st>>>(
+        s->map_x_k, s->map_x_mn, s->map_h, s->map_hht, s->map_w, p);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
