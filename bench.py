@@ -324,10 +324,65 @@ def run_gpu_arm(args):
                                   'sample': f'first {min(n, 1_000_000)} rows ({farcs} arcs), '
                                             f'{fdt:.2f} s'}}
 
+    # ---- hot path B beside it (N = 1): RolX NMF, BASELINE.json configs[4] ---------------------
+    if world == 1 and not args.no_nmf:
+        try:
+            del X0
+            torch.cuda.empty_cache()
+            line['nmf'] = nmf_section(device)
+        except Exception as exc:      # never lose the headline line to the secondary section
+            line['nmf'] = {'error': repr(exc)}
+
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def nmf_section(device, n=10_000_000, f=512, ranks=(4, 8, 16, 32), iters=10):
+    """ms per multiplicative-update iteration on X = 10M x 512 fp32 (synthetic U[0,1)), tcgen05
+    path, tol = 0 (no convergence pass in the timed region); algorithmic bytes n*f*4 + 2*n*r*4."""
+    from graphrole_b200.roles import factor
+    gen = torch.Generator(device=device).manual_seed(0)
+    X = torch.rand(n, f, device=device, generator=gen)
+    peak, _ = measured_peak_hbm()
+    rows = []
+    for r in ranks:
+        W = torch.rand(n, r, device=device, generator=gen) + 0.1
+        H = torch.rand(r, f, device=device, generator=gen) + 0.1
+        solver = factor.NmfSolver(n, f, r, device)
+        solver.update(X, W, H, max_iter=3, tol=0, want_error=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        solver.update(X, W, H, max_iter=iters, tol=0, want_error=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        alg = n * f * 4 + 2 * n * r * 4
+        flops = 4 * n * f * r + 4 * n * r * r + 2 * r * r * f
+        rows.append({'r': r, 'path': solver.last_path, 'ms_per_iter': ms,
+                     'alg_GBps': alg / ms / 1e6, 'frac_of_hbm_peak': alg / ms / 1e6 / peak,
+                     'alg_TFLOPs': flops / ms / 1e9})
+        solver.close()
+        del W, H
+    out = {'workload': f'X {n}x{f} fp32 U[0,1), shared random init, {iters} iterations',
+           'dtype': 'tf32 MMA / fp32 accumulate', 'per_rank': rows}
+    try:      # sklearn MU (the reference's solver) on a row sample, all BLAS threads
+        from sklearn.decomposition import _nmf as sk
+        m = 200_000
+        Xc = X[:m].double().cpu().numpy()
+        rng = np.random.RandomState(0)
+        W0, H0 = rng.rand(m, 32) + 0.1, rng.rand(32, f) + 0.1
+        t0 = time.perf_counter()
+        sk._fit_multiplicative_update(Xc, W0, H0, 'frobenius', max_iter=2, tol=0)
+        dt = (time.perf_counter() - t0) / 2
+        out['cpu_sklearn_f64'] = {'r': 32, 'rows': m, 's_per_iter_sample': dt,
+                                  's_per_iter_scaled_to_n': dt * n / m,
+                                  'cores': os.cpu_count()}
+    except Exception as exc:
+        out['cpu_sklearn_f64'] = {'error': repr(exc)}
+    return out
 
 
 def main():
@@ -339,6 +394,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-nmf', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':
