@@ -38,6 +38,9 @@ WORKLOAD_NAMES = {
     'c2': 'Erdos-Renyi |V|=1M |E|~20M (CSR nnz~40M), 32 features, 4 levels',
     'tiny': 'Barabasi-Albert |V|=200k m=20, 64 features, 5 levels (development only)',
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of one refex_gather_kernel launch, from the
+# `ncu --set full` capture committed as profiles/r1_ncu_refex_final_raw.csv (single GPU only)
+NCU_TRAFFIC_BYTES = {'c3': 91.29e9 + 5.49e9}
 METRIC = 'refex_aggregated_edges_x_features_per_sec'
 UNIT = 'arc*features/s'
 
@@ -263,6 +266,9 @@ def run_gpu_arm(args):
     kern_ms_avg = float(np.mean(kern_ms)) if kern_ms else float('nan')
     peak, peak_src = measured_peak_hbm()
     alg_bytes = algorithmic_bytes_per_level(engine.local_rows, engine.local_nnz, d)
+    nvlink_bytes = 0
+    if engine.exchange == 'peer':        # the mean rows also go to the world-1 peer replicas
+        nvlink_bytes = engine.local_rows * d * 4 * (world - 1)
     achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
 
     line = {
@@ -275,16 +281,27 @@ def run_gpu_arm(args):
                    'l2': 'inputs larger than L2 (feature matrix %.2f GB vs 126 MB L2)'
                          % (n * d * 4 / 1e9),
                    'parallelism': 'single GPU' if world == 1 else
-                   f'node-range sharded x{world}, nnz-balanced, all-gather per level',
+                   f'node-range sharded x{world}, nnz-balanced ranges, full input replica per GPU',
+                   'exchange': {'none': 'none (single GPU)',
+                                'peer': 'fused: gather kernel stores mean rows into every '
+                                        'replica over NVLink-mapped peer pointers + flag barrier',
+                                'nccl': 'all-gather of the mean rows after the kernel'}
+                   [engine.exchange] + (f' [{engine.exchange_note}]' if engine.exchange_note
+                                        else ''),
                    'value_with_undirected_edge_convention': value / 2},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                     'kernel': 'refex_gather_kernel', 'kernel_ms_avg': kern_ms_avg,
-                     'algorithmic_bytes_per_launch': alg_bytes},
+                     'frac': achieved / peak,
+                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
+                     'peak_source': peak_src,
+                     'kernel': 'refex_gather_kernel' if engine.exchange != 'peer'
+                     else 'refex_gather_bcast_kernel', 'kernel_ms_avg': kern_ms_avg,
+                     'algorithmic_bytes_per_launch': alg_bytes,
+                     'nvlink_store_bytes_per_launch': nvlink_bytes},
         'clocks': clocks.summary(),
         'gpu_launches': launches,
     }
 
+    engine.close()
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region (N = 1) -------
     if world == 1 and not args.no_e2e:
         del engine

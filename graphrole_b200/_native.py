@@ -32,6 +32,17 @@ SIGNATURES = {
                             POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     'gr_refex_aggregate_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
                                        c_void_p, c_void_p, c_int64, c_void_p]),
+    'gr_refex_aggregate_bcast_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64,
+                                             c_int64, c_void_p, POINTER(c_void_p), c_int32,
+                                             c_int64, c_void_p]),
+    'gr_peer_alloc': (c_int, [POINTER(c_void_p), c_int64, c_int, c_void_p]),
+    'gr_peer_open': (c_int, [POINTER(c_void_p), c_void_p, c_int]),
+    'gr_peer_close': (c_int, [c_void_p, c_int]),
+    'gr_peer_free': (c_int, [c_void_p, c_int]),
+    'gr_peer_barrier': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int64, c_double,
+                                c_void_p]),
+    'gr_peer_flag_words': (c_int64, []),
+    'gr_peer_barrier_status': (c_int, [c_void_p, POINTER(c_int64)]),
     'gr_refex_levels_host_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                          c_void_p, c_void_p]),
     'gr_nmf_create': (c_int, [POINTER(c_void_p), c_int64, c_int32, c_int32, c_int]),
@@ -205,6 +216,31 @@ class CsrHandle:
             row_lo, row_hi, ptrs[0], ptrs[1], ldo, _stream_ptr(stream)),
             'gr_refex_aggregate_f32')
 
+    def aggregate_bcast(self, X, out_sum, replica_ptrs, ldo, row_offset, stream=None):
+        """Fused level + exchange: mean rows of this handle's rows go to every replica.
+
+        replica_ptrs: base addresses (ints) of the [n_cols, ldo] fp32 replicas of the next
+        input matrix -- own and peer-mapped; row_offset = global row number of handle row 0.
+        out_sum: optional local [n_rows, d] tensor with row stride ldo."""
+        import torch
+        if X.dtype != torch.float32 or not X.is_cuda or X.dim() != 2 or X.stride(1) != 1:
+            raise ValueError('X must be a 2-D float32 CUDA tensor with unit column stride')
+        if X.shape[0] != self.n_cols:
+            raise ValueError(f'X has {X.shape[0]} rows, graph addresses {self.n_cols}')
+        d = X.shape[1]
+        sum_ptr = c_void_p(0)
+        if out_sum is not None:
+            if (out_sum.dtype != torch.float32 or tuple(out_sum.shape) != (self.n_rows, d)
+                    or out_sum.stride(1) != 1 or (self.n_rows > 1 and out_sum.stride(0) != ldo)):
+                raise ValueError(f'out_sum must be float32 [{self.n_rows}, {d}], row stride {ldo}')
+            sum_ptr = c_void_p(out_sum.data_ptr())
+        arr = (c_void_p * len(replica_ptrs))(*[c_void_p(int(p) + row_offset * ldo * 4)
+                                                for p in replica_ptrs])
+        check(load().gr_refex_aggregate_bcast_f32(
+            self._handle, c_void_p(X.data_ptr()), X.stride(0) if X.shape[0] > 1 else d, d,
+            0, self.n_rows, sum_ptr, arr, len(replica_ptrs), ldo, _stream_ptr(stream)),
+            'gr_refex_aggregate_bcast_f32')
+
     def levels_host(self, X_host, levels, recurse_on='mean', out_host=None, stream=None):
         """Host-buffer entry point: H2D of X, `levels` recursion levels, D2H of every level."""
         import torch
@@ -235,3 +271,77 @@ class CsrHandle:
             self.close()
         except Exception:
             pass
+
+
+class PeerBuffer:
+    """A device buffer other processes on the box can map (gr_peer_alloc).  `handle` is the
+    64-byte token to ship to the peers; PeerBuffer.open(token) maps a peer's buffer."""
+
+    def __init__(self, nbytes, device_index, _ptr=None, _owned=True):
+        self.nbytes = int(nbytes)
+        self.device_index = int(device_index)
+        self._owned = _owned
+        if _ptr is not None:
+            self.ptr = _ptr
+            self.handle = None
+            return
+        ptr = c_void_p()
+        token = ctypes.create_string_buffer(64)
+        check(load().gr_peer_alloc(byref(ptr), self.nbytes, self.device_index, token),
+              'gr_peer_alloc')
+        self.ptr = int(ptr.value)
+        self.handle = bytes(token.raw)
+
+    @classmethod
+    def open(cls, token, nbytes, device_index):
+        ptr = c_void_p()
+        buf = ctypes.create_string_buffer(bytes(token), 64)
+        check(load().gr_peer_open(byref(ptr), buf, int(device_index)), 'gr_peer_open')
+        return cls(nbytes, device_index, _ptr=int(ptr.value), _owned=False)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {'shape': (self.nbytes,), 'typestr': '|u1', 'data': (self.ptr, False),
+                'version': 3, 'strides': None}
+
+    def tensor(self, shape, dtype):
+        """torch view of the buffer (keeps this object alive through the array interface)."""
+        import torch
+        flat = torch.as_tensor(self, device=torch.device('cuda', self.device_index))
+        count = 1
+        for s in shape:
+            count *= int(s)
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        return flat[:count * itemsize].view(dtype).view(*shape)
+
+    def close(self):
+        if getattr(self, 'ptr', None):
+            lib = load()
+            if self._owned:
+                lib.gr_peer_free(c_void_p(self.ptr), self.device_index)
+            else:
+                lib.gr_peer_close(c_void_p(self.ptr), self.device_index)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def peer_flag_words():
+    return int(load().gr_peer_flag_words())
+
+
+def peer_barrier(flag_ptrs, rank, epoch, timeout_s=20.0, stream=None):
+    arr = (c_void_p * len(flag_ptrs))(*[c_void_p(int(p)) for p in flag_ptrs])
+    check(load().gr_peer_barrier(arr, len(flag_ptrs), rank, epoch, timeout_s, _stream_ptr(stream)),
+          'gr_peer_barrier')
+
+
+def peer_barrier_timed_out(own_flag_ptr):
+    v = c_int64()
+    check(load().gr_peer_barrier_status(c_void_p(int(own_flag_ptr)), byref(v)),
+          'gr_peer_barrier_status')
+    return int(v.value)

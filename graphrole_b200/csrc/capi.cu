@@ -153,8 +153,12 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
     std::vector<int64_t> rp((size_t)n_rows + 1);
     GR_CUDA_TRY(cudaMemcpy(rp.data(), rowptr_dev, rp.size() * sizeof(int64_t),
                            cudaMemcpyDeviceToHost));
-    if (rp[0] != 0)
-        return fail(GR_ERR_INVALID_GRAPH, "rowptr[0] = %lld, expected 0", (long long)rp[0]);
+    // rowptr[0] > 0 is a row-range shard that keeps a few leading colidx entries of the previous
+    // row so that its arcs sit at the same offsets modulo 32 as in the unsharded graph (the
+    // gather kernel's chunking, hence its fp32 summation order, depends on them)
+    if (rp[0] < 0 || rp[0] > nnz)
+        return fail(GR_ERR_INVALID_GRAPH, "rowptr[0] = %lld, expected 0 <= rowptr[0] <= nnz",
+                    (long long)rp[0]);
     if (rp[(size_t)n_rows] != nnz)
         return fail(GR_ERR_INVALID_GRAPH, "rowptr[n_rows] = %lld, expected nnz = %lld",
                     (long long)rp[(size_t)n_rows], (long long)nnz);

@@ -33,6 +33,7 @@ namespace {
 constexpr int kWarps = 8;      // 256 threads per CTA
 constexpr int kMinBlocks = 8;  // 32 registers/thread -> 64 resident warps per SM
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxReplicas = 16;
 
 struct RefexArgs {
     const int64_t* __restrict__ rowptr;
@@ -50,6 +51,15 @@ struct RefexArgs {
     float* __restrict__ partial;  // [n_segments, d], indexed by handle-global segment id
     int64_t n_seg_blocks;         // leading CTAs (blockIdx.x) that reduce hub segments
     int32_t rows_per_warp;
+};
+
+// Fused gather + broadcast (node-range sharded recursion): the mean rows are written into
+// `n_rep` replicas of the next level's input matrix -- this GPU's own and its peers', the latter
+// mapped over NVLink -- instead of one local buffer, so the exchange step of the level rides on
+// the gather kernel's own stores.  Pointers are rebased to handle-local row 0.
+struct Replicas {
+    float* mean[kMaxReplicas];
+    int32_t n_rep;
 };
 
 // ---- vector helpers -------------------------------------------------------------------
@@ -104,6 +114,20 @@ __device__ __forceinline__ void store_stream<4>(float* p, const float (&v)[4], f
 template <>
 __device__ __forceinline__ void store_stream<1>(float* p, const float (&v)[1], float scale) {
     __stcs(p, v[0] * scale);
+}
+
+// Replica stores (possibly to a peer GPU): default cache policy, write-back at L2 / posted over
+// NVLink.
+template <int VW>
+__device__ __forceinline__ void store_plain(float* p, const float (&v)[VW], float scale);
+template <>
+__device__ __forceinline__ void store_plain<4>(float* p, const float (&v)[4], float scale) {
+    *reinterpret_cast<float4*>(p) =
+        make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+}
+template <>
+__device__ __forceinline__ void store_plain<1>(float* p, const float (&v)[1], float scale) {
+    *p = v[0] * scale;
 }
 
 // ---- the warp's view of its contiguous colidx span --------------------------------------
@@ -180,9 +204,8 @@ __device__ __forceinline__ void reduce_arcs(ArcStream& s, uint32_t beg, uint32_t
 // CTAs [0, n_seg_blocks): one warp per hub segment (kHubSegment arcs of a long row -> fp32
 // partial); they lead the grid so the long warps start first and overlap the ordinary rows.
 // Remaining CTAs: rows_per_warp consecutive ordinary rows per warp.
-template <int LPR, int VW>
-__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
-refex_gather_kernel(const RefexArgs a) {
+template <int LPR, int VW, bool BCAST>
+__device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* rep) {
     constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
@@ -233,9 +256,29 @@ refex_gather_kernel(const RefexArgs a) {
         const int64_t o = (first + r) * a.ldo + col;
         // lane group 0 writes the sum block, group 1 (or the same lanes when LPR == 32) the mean
         if (a.out_sum && grp == 0) store_stream<VW>(a.out_sum + o, tot, 1.f);
-        if (a.out_mean && grp == (G >= 2 ? 1 : 0))
-            store_stream<VW>(a.out_mean + o, tot, deg ? __frcp_rn((float)deg) : 0.f);
+        if constexpr (BCAST) {
+            // lane group g writes replicas g, g + G, ...: remote stores are posted writes, the
+            // groups only split the issue slots
+            const float inv = deg ? __frcp_rn((float)deg) : 0.f;
+            for (int p = grp; p < rep->n_rep; p += G) store_plain<VW>(rep->mean[p] + o, tot, inv);
+        } else {
+            if (a.out_mean && grp == (G >= 2 ? 1 : 0))
+                store_stream<VW>(a.out_mean + o, tot, deg ? __frcp_rn((float)deg) : 0.f);
+        }
     }
+}
+
+template <int LPR, int VW>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
+refex_gather_kernel(const RefexArgs a) {
+    gather_body<LPR, VW, false>(a, nullptr);
+}
+
+// Same gather, mean rows broadcast to every replica (own + peers over NVLink).
+template <int LPR, int VW>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
+refex_gather_bcast_kernel(const RefexArgs a, const Replicas rep) {
+    gather_body<LPR, VW, true>(a, &rep);
 }
 
 // One warp per hub row: add the row's segment partials in fp64, in segment order.
@@ -243,7 +286,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict__ hub_seg_first,
                  const int64_t* __restrict__ rowptr, int64_t hub_lo, int64_t hub_hi,
                  const float* __restrict__ partial, int32_t d, float* __restrict__ out_sum,
-                 float* __restrict__ out_mean, int64_t ldo) {
+                 float* __restrict__ out_mean, int64_t ldo, const Replicas rep) {
     const int lane = threadIdx.x & 31;
     const int64_t h = hub_lo + (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (h >= hub_hi) return;
@@ -255,27 +298,33 @@ hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict_
         for (int64_t s = s0; s < s1; ++s) acc += (double)partial[s * d + c];
         if (out_sum) out_sum[row * ldo + c] = (float)acc;
         if (out_mean) out_mean[row * ldo + c] = (float)(acc / deg);
+        for (int p = 0; p < rep.n_rep; ++p) rep.mean[p][row * ldo + c] = (float)(acc / deg);
     }
 }
 
 // ---- launch plumbing --------------------------------------------------------------------
 template <int LPR, int VW>
-cudaError_t launch_gather(const RefexArgs& a, dim3 row_grid, dim3 seg_grid, cudaStream_t st) {
+cudaError_t launch_gather(const RefexArgs& a, const Replicas* rep, dim3 row_grid, dim3 seg_grid,
+                          cudaStream_t st) {
     dim3 grid(row_grid.x + seg_grid.x, row_grid.y, 1);
-    refex_gather_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a);
+    if (rep)
+        refex_gather_bcast_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a, *rep);
+    else
+        refex_gather_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }
 
 template <int VW>
-cudaError_t dispatch_lpr(int lpr, const RefexArgs& a, dim3 rg, dim3 sg, cudaStream_t st) {
+cudaError_t dispatch_lpr(int lpr, const RefexArgs& a, const Replicas* rep, dim3 rg, dim3 sg,
+                         cudaStream_t st) {
     switch (lpr) {
-        case 1: return launch_gather<1, VW>(a, rg, sg, st);
-        case 2: return launch_gather<2, VW>(a, rg, sg, st);
-        case 4: return launch_gather<4, VW>(a, rg, sg, st);
-        case 8: return launch_gather<8, VW>(a, rg, sg, st);
-        case 16: return launch_gather<16, VW>(a, rg, sg, st);
-        default: return launch_gather<32, VW>(a, rg, sg, st);
+        case 1: return launch_gather<1, VW>(a, rep, rg, sg, st);
+        case 2: return launch_gather<2, VW>(a, rep, rg, sg, st);
+        case 4: return launch_gather<4, VW>(a, rep, rg, sg, st);
+        case 8: return launch_gather<8, VW>(a, rep, rg, sg, st);
+        case 16: return launch_gather<16, VW>(a, rep, rg, sg, st);
+        default: return launch_gather<32, VW>(a, rep, rg, sg, st);
     }
 }
 
@@ -300,13 +349,17 @@ int ensure_floats(float** buf, size_t* have, size_t want) {
 
 }  // namespace
 
-extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, int32_t d,
-                                      int64_t row_lo, int64_t row_hi, float* out_sum,
-                                      float* out_mean, int64_t ldo, void* stream) {
+namespace {
+
+// One level over rows [row_lo, row_hi) of the handle.  rep == nullptr: plain outputs; otherwise
+// the mean rows go to every replica in *rep (out_mean is ignored) -- the fused exchange.
+int aggregate_impl(gr_csr_t* g, const float* X, int64_t ldx, int32_t d, int64_t row_lo,
+                   int64_t row_hi, float* out_sum, float* out_mean, int64_t ldo,
+                   const Replicas* rep, void* stream) {
     GR_REQUIRE(g != nullptr, "gr_refex_aggregate_f32: handle is NULL");
     GR_REQUIRE(d >= 1, "gr_refex_aggregate_f32: d = %d, need d >= 1", d);
     GR_REQUIRE(X != nullptr, "gr_refex_aggregate_f32: X is NULL");
-    GR_REQUIRE(out_sum != nullptr || out_mean != nullptr,
+    GR_REQUIRE(out_sum != nullptr || out_mean != nullptr || rep != nullptr,
                "gr_refex_aggregate_f32: both outputs are NULL");
     GR_REQUIRE(ldx >= d && ldo >= d, "gr_refex_aggregate_f32: ldx = %lld / ldo = %lld < d = %d",
                (long long)ldx, (long long)ldo, d);
@@ -349,8 +402,10 @@ extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, 
     a.n_seg_blocks = ceil_div<int64_t>(seg_hi - seg_lo, kWarps);
     a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", 16, 1, 31);
 
-    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) &&
-                      (!out_sum || aligned16(out_sum)) && (!out_mean || aligned16(out_mean));
+    bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) &&
+                (!out_sum || aligned16(out_sum)) && (!out_mean || aligned16(out_mean));
+    if (rep)
+        for (int p = 0; p < rep->n_rep; ++p) vec4 = vec4 && aligned16(rep->mean[p]);
     const int vw = vec4 ? 4 : 1;
     const int units = ceil_div<int>(d, vw);  // lanes needed to cover one feature row
     int lpr = vec4 ? 1 : 4;
@@ -364,21 +419,49 @@ extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, 
     dim3 row_grid((unsigned)row_blocks, (unsigned)col_tiles, 1);
     dim3 seg_grid((unsigned)a.n_seg_blocks, (unsigned)col_tiles, 1);
 
-    cudaError_t e = vec4 ? dispatch_lpr<4>(lpr, a, row_grid, seg_grid, st)
-                         : dispatch_lpr<1>(lpr, a, row_grid, seg_grid, st);
+    cudaError_t e = vec4 ? dispatch_lpr<4>(lpr, a, rep, row_grid, seg_grid, st)
+                         : dispatch_lpr<1>(lpr, a, rep, row_grid, seg_grid, st);
     if (e != cudaSuccess)
         return fail(GR_ERR_CUDA, "refex_gather_kernel launch failed: %s", cudaGetErrorString(e));
 
     if (hub_hi > hub_lo) {
         hub_fixup_kernel<<<(unsigned)ceil_div<int64_t>(hub_hi - hub_lo, kWarps), kWarps * 32, 0,
                            st>>>(g->d_hub_row, g->d_hub_seg_first, g->rowptr, hub_lo, hub_hi,
-                                 g->d_partial, d, out_sum, out_mean, ldo);
+                                 g->d_partial, d, out_sum, rep ? nullptr : out_mean, ldo,
+                                 rep ? *rep : Replicas{{}, 0});
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess)
             return fail(GR_ERR_CUDA, "hub_fixup_kernel launch failed: %s", cudaGetErrorString(e));
     }
     return GR_OK;
+}
+
+}  // namespace
+
+extern "C" int gr_refex_aggregate_f32(gr_csr_t* g, const float* X, int64_t ldx, int32_t d,
+                                      int64_t row_lo, int64_t row_hi, float* out_sum,
+                                      float* out_mean, int64_t ldo, void* stream) {
+    return aggregate_impl(g, X, ldx, d, row_lo, row_hi, out_sum, out_mean, ldo, nullptr, stream);
+}
+
+extern "C" int gr_refex_aggregate_bcast_f32(gr_csr_t* g, const float* X, int64_t ldx, int32_t d,
+                                            int64_t row_lo, int64_t row_hi, float* out_sum,
+                                            float* const* mean_replicas, int32_t n_replicas,
+                                            int64_t ldo, void* stream) {
+    GR_REQUIRE(mean_replicas != nullptr && n_replicas >= 1 && n_replicas <= kMaxReplicas,
+               "gr_refex_aggregate_bcast_f32: need 1..%d replica pointers, got %d", kMaxReplicas,
+               n_replicas);
+    Replicas rep;
+    rep.n_rep = n_replicas;
+    for (int p = 0; p < kMaxReplicas; ++p) {
+        rep.mean[p] = p < n_replicas ? mean_replicas[p] : nullptr;
+        GR_REQUIRE(p >= n_replicas || rep.mean[p] != nullptr,
+                   "gr_refex_aggregate_bcast_f32: replica %d is NULL", p);
+        GR_REQUIRE(p >= n_replicas || rep.mean[p] != X,
+                   "gr_refex_aggregate_bcast_f32: replica %d aliases X", p);
+    }
+    return aggregate_impl(g, X, ldx, d, row_lo, row_hi, out_sum, nullptr, ldo, &rep, stream);
 }
 
 extern "C" int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,

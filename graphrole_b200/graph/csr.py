@@ -171,11 +171,17 @@ class CSRGraph:
         return self._handles[key]
 
     def row_slice(self, lo: int, hi: int) -> 'CSRGraph':
-        """Rows [lo, hi) as a shard: rowptr rebased to 0, colidx still addresses all n nodes."""
+        """Rows [lo, hi) as a shard; colidx still addresses all n nodes.  The colidx slice starts
+        at the 32-arc boundary at or below the first arc (rowptr[0] of the shard is that
+        remainder, < 32): the gather kernel reads colidx in 32-entry chunks aligned to absolute
+        arc positions and its fp32 summation order follows the chunking, so a shard laid out
+        this way gives bit-identical results to the unsharded graph."""
         rp = self.rowptr[lo:hi + 1]
         a, b = int(rp[0]), int(rp[-1])
-        shard = CSRGraph(rp - a, self.colidx[a:b], directed=True)
+        a0 = a - a % 32
+        shard = CSRGraph(rp - a0, self.colidx[a0:b], directed=True)
         shard.n_cols = self.n
+        shard.nnz = b - a            # arcs of the shard's rows (the slice holds a - a0 more)
         return shard
 
     def __repr__(self):

@@ -4,8 +4,11 @@ Path A shards by output row: rank g owns the contiguous node range [lo_g, hi_g) 
 chosen so every rank traverses the same number of arcs -- power-law graphs put the hubs at the
 front), holds that slice of the CSR, a full replica of the current level's input matrix, and
 produces its rows of the next level.  The one exchange step per level is an all-gather of the
-block the recursion continues on: every rank writes its mean rows
-straight into its slice of the next full input matrix and the slices are exchanged in place.
+block the recursion continues on.  Primary form: the exchange is fused
+into the gather kernel -- every mean row is stored into all ranks' replicas of the next input
+matrix through NVLink-mapped peer pointers, and a flag barrier in the same mapped memory
+separates the levels (PeerReplicas).  Alternative form: every rank writes its slice and the
+slices are exchanged in place by a torch.distributed all-gather (exchange_rows).
 """
 from typing import List, Optional, Tuple
 
@@ -42,16 +45,88 @@ def exchange_rows(full: torch.Tensor, ranges: List[Tuple[int, int]], rank: int, 
         w.wait()
 
 
+class PeerReplicas:
+    """Two full [n, d] fp32 replicas of the level input plus the barrier flags, in ONE
+    peer-mappable buffer per rank (gr_peer_alloc), with every other rank's buffer mapped into
+    this process.  Layout: replica 0 | replica 1 | flag words (256-byte aligned offsets)."""
+
+    def __init__(self, n: int, d: int, world: int, rank: int, device: torch.device):
+        import torch.distributed as dist
+        from graphrole_b200 import _native
+        self.n, self.d, self.world, self.rank = n, d, world, rank
+        self.replica_bytes = (n * d * 4 + 255) // 256 * 256
+        self.flag_offset = 2 * self.replica_bytes
+        nbytes = self.flag_offset + 8 * _native.peer_flag_words()
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        self.own = _native.PeerBuffer(nbytes, dev)
+        # the flag words live right behind the replicas
+        self.flags = torch.as_tensor(self.own, device=device)[self.flag_offset:].view(torch.int64)
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        tokens = [None] * world
+        dist.all_gather_object(tokens, self.own.handle)     # also orders the zeroing
+        self.buffers = []
+        for q in range(world):
+            self.buffers.append(self.own if q == rank
+                                else _native.PeerBuffer.open(tokens[q], nbytes, dev))
+        self.epoch = 0
+        flat = torch.as_tensor(self.own, device=device)
+        self.replicas = [flat[i * self.replica_bytes: i * self.replica_bytes + n * d * 4]
+                         .view(torch.float32).view(n, d) for i in range(2)]
+
+    def replica_ptrs(self, which: int):
+        return [b.ptr + which * self.replica_bytes for b in self.buffers]
+
+    def flag_ptrs(self):
+        return [b.ptr + self.flag_offset for b in self.buffers]
+
+    def barrier(self, stream=None):
+        from graphrole_b200 import _native
+        self.epoch += 1
+        _native.peer_barrier(self.flag_ptrs(), self.rank, self.epoch, stream=stream)
+
+    def timed_out(self) -> int:
+        from graphrole_b200 import _native
+        return _native.peer_barrier_timed_out(self.own.ptr + self.flag_offset)
+
+    def close(self):
+        """Unmap the peers' buffers, then (after everyone has) release the own one."""
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        for q, b in enumerate(self.buffers):
+            if q != self.rank:
+                b.close()
+        if dist.is_initialized():
+            dist.barrier()
+        self.replicas = None
+        self.flags = None
+        self.own.close()
+
+
 class ShardedRefex:
     """Runs `levels` recursion levels (schedule alpha: recurse on the mean block) on this
-    rank's node range; world == 1 is the plain single-GPU path with no exchange."""
+    rank's node range; world == 1 is the plain single-GPU path with no exchange.
 
-    def __init__(self, graph: CSRGraph, d: int, world: int = 1, rank: int = 0, group=None):
+    exchange (world > 1):
+      'peer'  (default) the gather kernel stores every mean row into all ranks' replicas of the
+              next input matrix over NVLink-mapped pointers (gr_refex_aggregate_bcast_f32) and
+              a flag barrier in the same mapped memory separates the levels -- no collective
+              library call on the data path;
+      'nccl'  the kernel writes the own slice and a torch.distributed all-gather (or one
+              broadcast per owner for uneven ranges) exchanges the slices in place.
+    If the CUDA IPC mapping cannot be set up on every rank, all ranks drop to 'nccl' together
+    and `exchange_note` says why."""
+
+    def __init__(self, graph: CSRGraph, d: int, world: int = 1, rank: int = 0, group=None,
+                 exchange: Optional[str] = None):
         self.d = d
         self.world = world
         self.rank = rank
         self.group = group
         self.n = graph.n
+        self.exchange = 'none'
+        self.exchange_note = ''
+        self.peers = None
         device = graph.rowptr.device
         if world == 1:
             self.ranges = [(0, graph.n)]
@@ -59,13 +134,33 @@ class ShardedRefex:
             self.local_rows, self.local_nnz = graph.n, graph.nnz
             self.out = [torch.empty((graph.n, 2 * d), dtype=torch.float32, device=device)
                         for _ in range(2)]
-        else:
-            self.ranges = nnz_balanced_ranges(graph.rowptr, world)
-            lo, hi = self.ranges[rank]
-            self.shard = graph.row_slice(lo, hi)
-            self.handle = self.shard.handle(device)
-            self.local_rows, self.local_nnz = hi - lo, self.shard.nnz
-            self.sums = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
+            return
+        import os
+        self.ranges = nnz_balanced_ranges(graph.rowptr, world)
+        lo, hi = self.ranges[rank]
+        self.shard = graph.row_slice(lo, hi)
+        self.handle = self.shard.handle(device)
+        self.local_rows, self.local_nnz = hi - lo, self.shard.nnz
+        self.sums = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
+        exchange = exchange or os.environ.get('GR_SHARD_EXCHANGE', 'peer')
+        if exchange not in ('peer', 'nccl'):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        if exchange == 'peer':
+            import torch.distributed as dist
+            ok, why = 1, ''
+            try:
+                self.peers = PeerReplicas(graph.n, d, world, rank, device)
+            except Exception as exc:      # every rank must take the same path: vote below
+                ok, why = 0, repr(exc)
+            vote = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+            if int(vote.item()) == 0:
+                if self.peers is not None:
+                    self.peers = None
+                exchange = 'nccl'
+                self.exchange_note = 'peer mapping failed on some rank, using nccl: ' + why
+        self.exchange = exchange
+        if exchange == 'nccl':
             self.full = [torch.empty((graph.n, d), dtype=torch.float32, device=device)
                          for _ in range(2)]
 
@@ -74,6 +169,10 @@ class ShardedRefex:
         d = self.d
         cur = X0
         last = None
+        if self.exchange == 'peer':
+            # the own replica 0 is the level-0 input (every rank holds the same X0)
+            self.peers.replicas[0].copy_(X0)
+            cur = self.peers.replicas[0]
         for level in range(levels):
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
@@ -86,6 +185,16 @@ class ShardedRefex:
                     events.append((e0, e1))
                 cur = out[:, d:]
                 last = (out[:, :d], out[:, d:])
+            elif self.exchange == 'peer':
+                lo, hi = self.ranges[self.rank]
+                which = (level + 1) & 1
+                self.handle.aggregate_bcast(cur, self.sums, self.peers.replica_ptrs(which), d, lo)
+                if events is not None:
+                    e1.record()
+                    events.append((e0, e1))
+                self.peers.barrier()
+                cur = self.peers.replicas[which]
+                last = (self.sums, cur[lo:hi])
             else:
                 lo, hi = self.ranges[self.rank]
                 nxt = self.full[level & 1]
@@ -97,3 +206,10 @@ class ShardedRefex:
                 cur = nxt
                 last = (self.sums, nxt[lo:hi])
         return last
+
+    def close(self):
+        if self.peers is not None:
+            if self.peers.timed_out():
+                raise RuntimeError(f'peer barrier timed out at epoch {self.peers.timed_out()}')
+            self.peers.close()
+            self.peers = None

@@ -59,7 +59,10 @@ int64_t gr_kernel_launch_count(void);
  *
  * n_rows  rows held by this handle (a node-range shard holds a slice of the rows)
  * n_cols  number of rows of the feature matrices that colidx may address (global node count)
- * rowptr  int64[n_rows + 1], rowptr[0] == 0, rowptr[n_rows] == nnz, non-decreasing
+ * rowptr  int64[n_rows + 1], non-decreasing, rowptr[n_rows] == nnz; rowptr[0] is 0 for a whole
+ *         graph and may be in (0, 32) for a row-range shard that keeps the colidx entries back to
+ *         the previous 32-arc boundary: the kernel's summation order depends on arc offsets
+ *         modulo 32, so such a shard reproduces the unsharded results bit for bit
  * colidx  int32[nnz], values in [0, n_cols)
  * The arrays are NOT copied: they must stay valid and unchanged until gr_csr_destroy().
  * flags:
@@ -101,6 +104,47 @@ int gr_refex_aggregate_f32(gr_csr_t* g, const float* X_dev, int64_t ldx, int32_t
                            int64_t row_lo, int64_t row_hi,
                            float* out_sum_dev, float* out_mean_dev, int64_t ldo,
                            void* stream);
+
+/* ---- path A, node-range sharded across the GPUs of one box ----------
+ * The reference has no distributed path (single-process Python; graphrole/features/extract.py
+ * :77-87 simply calls _get_next_features once per level).  Sharded by output row, level l+1
+ * needs ALL rows of level l's recursed block on every GPU -- the one exchange step of the
+ * path.  gr_refex_aggregate_bcast_f32 fuses that exchange into the gather kernel: it is
+ * gr_refex_aggregate_f32 whose mean rows are stored into n_replicas copies of the next input
+ * matrix (this GPU's and its peers', mapped with gr_peer_open) instead of one out_mean buffer.
+ *   mean_replicas  host array of n_replicas (<= 16) device pointers, each rebased to
+ *                  handle-local row 0 (replica_base + shard_row_offset * ldo), row stride ldo
+ *   out_sum        optional local sum rows (row stride ldo as well)
+ * Results are bit-identical to gr_refex_aggregate_f32.  The caller orders levels across GPUs
+ * with gr_peer_barrier (or any collective) on the same stream. */
+int gr_refex_aggregate_bcast_f32(gr_csr_t* g, const float* X_dev, int64_t ldx, int32_t d,
+                                 int64_t row_lo, int64_t row_hi, float* out_sum_dev,
+                                 float* const* mean_replicas, int32_t n_replicas, int64_t ldo,
+                                 void* stream);
+
+/* Device buffers another process on the same box can map (cudaMalloc + CUDA IPC).
+ * gr_peer_alloc   allocates `bytes` on `device` and fills the 64-byte handle to ship to the
+ *                 other ranks (any byte transport: torch.distributed.all_gather_object, a file)
+ * gr_peer_open    maps a peer's buffer into this process (peer access over NVLink is enabled on
+ *                 first use); gr_peer_close unmaps it; gr_peer_free releases an own buffer. */
+typedef struct { unsigned char bytes[64]; } gr_ipc_handle_t;
+
+int gr_peer_alloc(void** dev_ptr_out, int64_t bytes, int device, gr_ipc_handle_t* handle_out);
+int gr_peer_open(void** dev_ptr_out, const gr_ipc_handle_t* handle, int device);
+int gr_peer_close(void* dev_ptr, int device);
+int gr_peer_free(void* dev_ptr, int device);
+
+/* Stream-ordered barrier across the ranks of a box through flags in peer-mapped memory.
+ * flag_arrays[q] = rank q's flag array (gr_peer_flag_words() zero-initialised uint64 words in a
+ * gr_peer_alloc buffer; the own one at index `rank`).  Every rank calls it with the same,
+ * strictly increasing `epoch` (>= 1).  Work enqueued on `stream` after the call starts only
+ * when every rank's work enqueued before its call has completed, peer stores included.
+ * A rank that does not arrive within timeout_s (<= 0: 20 s) makes the kernel give up instead of
+ * hanging the GPU; gr_peer_barrier_status then returns the epoch that timed out (0 = none). */
+int gr_peer_barrier(void* const* flag_arrays, int32_t n_ranks, int32_t rank, int64_t epoch,
+                    double timeout_s, void* stream);
+int64_t gr_peer_flag_words(void);
+int gr_peer_barrier_status(const void* own_flag_array, int64_t* timed_out_epoch);
 
 /* Host-buffer variant (the call a ctypes binding inside the reference would make with
  * DataFrame.values): copies X (n_cols x d, row stride ldx) to the device, runs `levels`

@@ -268,3 +268,89 @@ def test_larger_random_graph_properties(n, deg, d):
     got = ox.cpu().numpy()[rows]
     np.testing.assert_allclose(got[:, :d], S, rtol=RTOL)
     np.testing.assert_allclose(got[:, d:], M, rtol=RTOL)
+
+
+# ---- node-range shards and the fused gather + broadcast kernel -------
+
+def test_row_slice_shards_reproduce_the_unsharded_bits():
+    """A shard laid out by CSRGraph.row_slice (colidx slice starting on a 32-arc boundary) must
+    give bit-identical rows: sharding may not change results."""
+    from graphrole_b200.graph.generators import barabasi_albert_csr
+    from graphrole_b200.shard import nnz_balanced_ranges
+    g = barabasi_albert_csr(120_000, 9, seed=4, device='cuda:0')     # has hub rows
+    X = torch.rand(g.n, 64, device='cuda:0') * 2 - 0.5
+    full = g.handle('cuda:0').aggregate(X)
+    for world in (2, 3, 8):
+        for lo, hi in nnz_balanced_ranges(g.rowptr, world):
+            shard = g.row_slice(lo, hi)
+            part = shard.handle('cuda:0').aggregate(X)
+            assert torch.equal(part, full[lo:hi]), (world, lo, hi)
+
+
+@pytest.mark.parametrize('d,n_rep', [(64, 1), (64, 3), (64, 8), (32, 2), (12, 5), (7, 3), (128, 4)])
+def test_fused_broadcast_kernel_matches_plain_kernel(d, n_rep):
+    """gr_refex_aggregate_bcast_f32 with every replica on this GPU: each replica receives the
+    shard's mean rows at the shard's global row offset, nothing else is touched, and the values
+    are bit-identical to gr_refex_aggregate_f32 (hub rows included)."""
+    from graphrole_b200.graph.generators import barabasi_albert_csr
+    g = barabasi_albert_csr(60_000, 9, seed=6, device='cuda:0')
+    X = torch.rand(g.n, d, device='cuda:0')
+    full = g.handle('cuda:0').aggregate(X)
+    lo, hi = 11, 41_234
+    shard = g.row_slice(lo, hi)
+    assert shard.handle('cuda:0').info()['n_hub_rows'] > 0
+    reps = [torch.full((g.n, d), -7.0, device='cuda:0') for _ in range(n_rep)]
+    sums = torch.empty((hi - lo, d), device='cuda:0')
+    shard.handle('cuda:0').aggregate_bcast(X, sums, [r.data_ptr() for r in reps], d, lo)
+    torch.cuda.synchronize()
+    assert torch.equal(sums, full[lo:hi, :d])
+    for r in reps:
+        assert torch.equal(r[lo:hi], full[lo:hi, d:])
+        assert bool((r[:lo] == -7.0).all()) and bool((r[hi:] == -7.0).all())
+
+
+def test_fused_broadcast_rejects_bad_arguments():
+    g = CSRGraph.from_edges([0, 1], [1, 2], n=3)
+    h = g.handle('cuda:0')
+    X = torch.ones(3, 4, device='cuda:0')
+    with pytest.raises(ValueError):
+        h.aggregate_bcast(X, None, [], 4, 0)                       # no replicas
+    with pytest.raises(ValueError):
+        h.aggregate_bcast(X, None, [X.data_ptr()], 4, 0)           # replica aliases X
+    with pytest.raises(ValueError):
+        h.aggregate_bcast(X, None, [X.data_ptr() + 4096] * 17, 4, 0)   # more than 16 replicas
+
+
+def test_peer_barrier_single_rank_and_timeout_flag():
+    """The flag barrier with one rank completes immediately; waiting for an epoch nobody
+    publishes gives up after the timeout and reports it instead of hanging."""
+    words = _native.peer_flag_words()
+    buf = _native.PeerBuffer(8 * words, 0)
+    flags = buf.tensor((words,), torch.int64)
+    flags.zero_()
+    torch.cuda.synchronize()
+    _native.peer_barrier([buf.ptr], 0, 1)
+    torch.cuda.synchronize()
+    assert int(flags[0]) == 1 and _native.peer_barrier_timed_out(buf.ptr) == 0
+    # two "ranks" sharing one flag array: slot 1 never gets epoch 2 -> timeout path
+    _native.peer_barrier([buf.ptr, buf.ptr], 0, 2, timeout_s=0.05)
+    torch.cuda.synchronize()
+    assert _native.peer_barrier_timed_out(buf.ptr) == 2
+    del flags
+    buf.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one box')
+def test_two_gpu_sharded_recursion_is_bit_identical():
+    """torchrun, one rank per GPU: fused peer-store exchange and the all-gather exchange both
+    reproduce the single-GPU recursion bit for bit (tools/check_sharded.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', '29731',
+         os.path.join(root, 'tools', 'check_sharded.py'), '--n', '200000', '--levels', '3'],
+        capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'SHARDED CHECK OK' in res.stdout, res.stdout + res.stderr

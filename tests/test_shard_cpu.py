@@ -37,9 +37,14 @@ def test_ranges_degenerate():
 def test_row_slice_keeps_global_columns():
     g = erdos_renyi_csr(2000, 10000, seed=2, device='cpu')
     s = g.row_slice(500, 1200)
-    assert s.n == 700 and s.n_cols == 2000 and int(s.rowptr[0]) == 0
     rp, ci = g.host_arrays()
-    np.testing.assert_array_equal(s.colidx.numpy(), ci[rp[500]:rp[1200]])
+    pad = int(rp[500]) % 32      # the slice starts at the 32-arc boundary below the first arc
+    assert s.n == 700 and s.n_cols == 2000 and int(s.rowptr[0]) == pad
+    assert s.nnz == rp[1200] - rp[500]
+    srp, sci = s.host_arrays()
+    np.testing.assert_array_equal(sci[pad:], ci[rp[500]:rp[1200]])
+    np.testing.assert_array_equal(np.diff(srp), np.diff(rp[500:1201]))
+    assert int(srp[-1]) == sci.size
 
 
 def _free_port():
@@ -62,6 +67,7 @@ def _worker(rank, world, port, levels, equal_rows, ret):
         lo, hi = ranges[rank]
         shard = g.row_slice(lo, hi)
         rp, ci = shard.host_arrays()
+        rp, ci = rp - rp[0], ci[rp[0]:]      # drop the 32-arc alignment pad of the slice
         cur = X0
         for _ in range(levels):
             nxt = torch.full((g.n, d), float('nan'), dtype=torch.float64)
