@@ -85,7 +85,8 @@ struct TcParams {
     float* part_wtw;     // [grid, 32, r]
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
-                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs
+                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs, 16 experiment: P1 reads
+                         // its K-major operand from tiles loaded with the 32-byte-atom swizzle
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -307,7 +308,8 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     if (g < 7) GR_TRACE(0, i, 1 + g);
                     mbar_expect_tx(bar(B_FULL_A + st), kStageABytes);
                     for (int c = 0; c < kStageABoxes; ++c)
-                        tma_load_2d(s_ra + st * kStageABytes + c * kBoxBytes, &map_x_k,
+                        tma_load_2d(s_ra + st * kStageABytes + c * kBoxBytes,
+                                    (p.debug & 16) ? &map_x_mn : &map_x_k,
                                     (g * kStageABoxes + c) * kBoxCols, row, bar(B_FULL_A + st));
                 }
             }
@@ -361,7 +363,9 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if (!(p.debug & 1))
-                                tc_mma_tf32(d1, make_desc(a0 + k * 32, 16, 1024, kLayoutSw128),
+                                tc_mma_tf32(d1, make_desc(a0 + k * 32, 16, 1024,
+                                                          (p.debug & 16) ? kLayoutSw128Base32
+                                                                         : kLayoutSw128),
                                             make_desc(b0 + k * 32, 16, 1024, kLayoutSw128),
                                             kIdescP1, (g | c | k) != 0);
                         }

@@ -293,10 +293,10 @@ def test_fused_broadcast_kernel_matches_plain_kernel(d, n_rep):
     shard's mean rows at the shard's global row offset, nothing else is touched, and the values
     are bit-identical to gr_refex_aggregate_f32 (hub rows included)."""
     from graphrole_b200.graph.generators import barabasi_albert_csr
-    g = barabasi_albert_csr(60_000, 9, seed=6, device='cuda:0')
+    g = barabasi_albert_csr(300_000, 10, seed=6, device='cuda:0')   # first rows are hubs
     X = torch.rand(g.n, d, device='cuda:0')
     full = g.handle('cuda:0').aggregate(X)
-    lo, hi = 11, 41_234
+    lo, hi = 1, 141_234
     shard = g.row_slice(lo, hi)
     assert shard.handle('cuda:0').info()['n_hub_rows'] > 0
     reps = [torch.full((g.n, d), -7.0, device='cuda:0') for _ in range(n_rep)]
