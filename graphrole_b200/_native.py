@@ -50,6 +50,17 @@ SIGNATURES = {
     'gr_nmf_mu_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_double,
                               c_int32, c_int32, POINTER(c_int32), POINTER(c_double), c_void_p]),
     'gr_nmf_last_path': (c_int, [c_void_p]),
+    'gr_pruner_create': (c_int, [POINTER(c_void_p), c_int64, c_int]),
+    'gr_pruner_destroy': (c_int, [c_void_p]),
+    'gr_prune_bin_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p,
+                                 c_int64, c_void_p]),
+    'gr_prune_bin_f64': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p,
+                                 c_int64, c_void_p]),
+    'gr_prune_pairwise_gap_i32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                          c_void_p]),
+    'gr_level0_features_f64': (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_void_p]),
     'gr_nmf_error_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  POINTER(c_double), c_void_p]),
 }
@@ -345,3 +356,102 @@ def peer_barrier_timed_out(own_flag_ptr):
     check(load().gr_peer_barrier_status(c_void_p(int(own_flag_ptr)), byref(v)),
           'gr_peer_barrier_status')
     return int(v.value)
+
+
+class Pruner:
+    """Owner of a gr_pruner_t*: vertical log binning of feature columns and the pairwise
+    Chebyshev gaps of the binned columns, for matrices of `n_rows` rows on one device."""
+
+    def __init__(self, n_rows, device):
+        import torch
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise NativeLibraryError('the pruning kernels run on CUDA devices only')
+        self.device = device if device.index is not None else \
+            torch.device('cuda', torch.cuda.current_device())
+        self.n_rows = int(n_rows)
+        handle = c_void_p()
+        check(load().gr_pruner_create(byref(handle), self.n_rows, self.device.index),
+              'gr_pruner_create')
+        self._handle = handle
+
+    def bin_columns(self, X, frac=0.5, out=None, stream=None):
+        """X: [n_rows, d] float32 / float64 CUDA tensor, unit column stride.  Returns the binned
+        columns as a COLUMN-major int32 tensor of shape [d, n_rows]."""
+        import torch
+        if not X.is_cuda or X.dim() != 2 or X.dtype not in (torch.float32, torch.float64):
+            raise ValueError('X must be a 2-D float32/float64 CUDA tensor')
+        if X.shape[0] != self.n_rows:
+            raise ValueError(f'X has {X.shape[0]} rows, the pruner was created for {self.n_rows}')
+        d = X.shape[1]
+        if d > 1 and X.stride(1) != 1:
+            raise ValueError('X must have unit column stride')
+        if out is None:
+            out = torch.empty((d, self.n_rows), dtype=torch.int32, device=X.device)
+        if tuple(out.shape) != (d, self.n_rows) or out.dtype != torch.int32 \
+                or not out.is_contiguous():
+            raise ValueError(f'out must be a contiguous int32 [{d}, {self.n_rows}] tensor')
+        fn = load().gr_prune_bin_f32 if X.dtype == torch.float32 else load().gr_prune_bin_f64
+        ldx = X.stride(0) if X.shape[0] > 1 else max(d, 1)
+        with torch.cuda.device(self.device):
+            check(fn(self._handle, c_void_p(X.data_ptr()), ldx, d, float(frac),
+                     c_void_p(out.data_ptr()), self.n_rows, _stream_ptr(stream)), 'gr_prune_bin')
+        return out
+
+    def pairwise_gaps(self, bins, stream=None):
+        """bins: [d, n_rows] int32 (bin_columns output).  Returns int32 [d, d]: max over rows of
+        |bins[i] - bins[j]|."""
+        import torch
+        if not bins.is_cuda or bins.dtype != torch.int32 or bins.dim() != 2 \
+                or not bins.is_contiguous() or bins.shape[1] != self.n_rows:
+            raise ValueError(f'bins must be a contiguous int32 CUDA [d, {self.n_rows}] tensor')
+        d = bins.shape[0]
+        gap = torch.empty((d, d), dtype=torch.int32, device=bins.device)
+        with torch.cuda.device(self.device):
+            check(load().gr_prune_pairwise_gap_i32(self._handle, c_void_p(bins.data_ptr()),
+                                                   self.n_rows, d, c_void_p(gap.data_ptr()),
+                                                   _stream_ptr(stream)),
+                  'gr_prune_pairwise_gap_i32')
+        return gap
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().gr_pruner_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def level0_features(rowptr, colidx, weights=None, directed=False, stream=None):
+    """gr_level0_features_f64 on CUDA tensors.  Returns a dict of float64 [n] tensors:
+    out_weight, in_weight (directed only), diag, internal, external."""
+    import torch
+    if not (rowptr.is_cuda and colidx.is_cuda):
+        raise NativeLibraryError('the level-0 kernels run on CUDA tensors only (no CPU fallback)')
+    if rowptr.dtype != torch.int64 or colidx.dtype != torch.int32:
+        raise ValueError('rowptr must be int64 and colidx int32')
+    rowptr, colidx = rowptr.contiguous(), colidx.contiguous()
+    n, nnz = rowptr.numel() - 1, colidx.numel()
+    dev = rowptr.device
+    if weights is not None:
+        weights = weights.to(dev, torch.float64).contiguous()
+        if weights.numel() != nnz:
+            raise ValueError('weights must have one entry per arc')
+    out = {k: torch.empty(n, dtype=torch.float64, device=dev)
+           for k in ('out_weight', 'diag', 'internal', 'external')}
+    if directed:
+        out['in_weight'] = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(load().gr_level0_features_f64(
+            n, nnz, c_void_p(rowptr.data_ptr()), c_void_p(colidx.data_ptr() if nnz else 0),
+            c_void_p(weights.data_ptr() if weights is not None else 0), int(bool(directed)),
+            c_void_p(out['out_weight'].data_ptr()),
+            c_void_p(out['in_weight'].data_ptr() if directed else 0),
+            c_void_p(out['diag'].data_ptr()), c_void_p(out['internal'].data_ptr()),
+            c_void_p(out['external'].data_ptr()), dev.index or 0, _stream_ptr(stream)),
+            'gr_level0_features_f64')
+    return out

@@ -1,0 +1,233 @@
+// Level-0 ("generation 0") neighbourhood features straight from the CSR arrays
+// ("next" #2).
+//
+// The reference builds them with one nx.ego_graph + nx.edge_boundary per node
+// (graphrole/graph/interface/networkx.py:48-83; 3.9 ms per node measured).  With W the weighted
+// out-adjacency and ego(i) = {i} U N_out(i):
+//
+//   out_w(i)   = sum_v W[i, v]            in_w(i) = sum_u W[u, i]          diag(i) = W[i, i]
+//   T(i)       = sum_{u in ego(i)} sum_{v in ego(i)} W[u, v]
+//              = out_w(i) + sum_{u in N(i), u != i} <row u restricted to ego(i)>
+//   internal_i = T(i)                                      directed  (arcs inside the egonet)
+//              = (T(i) + sum_{u in ego(i)} diag(u)) / 2    undirected (each edge once)
+//   external_i = sum_{u in ego(i)} out_w(u) - T(i)
+//
+// (the closed forms of graphrole_b200/graph/level0.py, checked there against the reference's
+// golden level-0 tables).  The restricted row sums are sorted-list intersections: for the arc
+// (i, u) the shorter of row u / row i is walked by an 8-lane group and each entry is looked up in
+// the longer one by binary search, so an arc costs min(deg) * log(max deg) -- hubs do not square.
+// Eight lanes per row, four rows per warp; all sums in fp64 with a fixed reduction order (exact
+// for integer weights); only in_w uses atomics.  Integer / index work, bound by L2 latency of the
+// dependent binary-search loads, not by HBM.
+
+#include "common.cuh"
+
+using namespace gr;
+
+namespace {
+
+constexpr int kLanes = 8;        // lanes per arc group
+constexpr int kBigRow = 1024;    // rows at least this long get a whole CTA
+
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, kLanes);
+    return v;
+}
+
+// position of `v` in colidx[lo, hi) (ascending) or -1
+__device__ __forceinline__ int64_t find(const int32_t* __restrict__ colidx, int64_t lo, int64_t hi,
+                                        int32_t v) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int32_t c = colidx[mid];
+        if (c < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;   // caller checks bounds + equality
+}
+
+__global__ void row_stats_kernel(int64_t n, const int64_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ colidx,
+                                 const double* __restrict__ w, double* __restrict__ out_w,
+                                 double* __restrict__ in_w, double* __restrict__ diag) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = gid / kLanes;
+    const int sub = (int)(gid % kLanes);
+    const unsigned mask = 0xffffffffu;
+    const bool valid = i < n;
+    const int64_t a = valid ? rowptr[i] : 0, b = valid ? rowptr[i + 1] : 0;
+    double s = 0.0, dg = 0.0;
+    for (int64_t k = a + sub; k < b; k += kLanes) {
+        const double wk = w ? w[k] : 1.0;
+        const int32_t v = colidx[k];
+        s += wk;
+        if (v == i) dg += wk;
+        if (in_w) atomicAdd(in_w + v, wk);
+    }
+    s = group_sum(s, mask);
+    dg = group_sum(dg, mask);
+    if (valid && sub == 0) {
+        out_w[i] = s;
+        diag[i] = dg;
+    }
+}
+
+// Partial sums of one row's egonet terms: this lane is lane `sub` of arc-group `grp` out of
+// `n_grp` groups working on row i (group g takes arcs g, g + n_grp, ...).
+struct EgoPartial { double t, eo, ed; };
+
+__device__ __forceinline__ EgoPartial ego_partial(int64_t i, int sub, int grp, int n_grp,
+                                                  const int64_t* __restrict__ rowptr,
+                                                  const int32_t* __restrict__ colidx,
+                                                  const double* __restrict__ w,
+                                                  const double* __restrict__ out_w,
+                                                  const double* __restrict__ diag) {
+    EgoPartial r = {0.0, 0.0, 0.0};
+    const int64_t ia = rowptr[i], ib = rowptr[i + 1];
+    const int32_t self = (int32_t)i;
+    // is i its own neighbour (self loop)?
+    const int64_t ps = find(colidx, ia, ib, self);
+    const bool has_self = ps < ib && colidx[ps] == self;
+    for (int64_t k = ia + grp; k < ib; k += n_grp) {
+        const int32_t u = colidx[k];
+        if (u == self) continue;                 // the u = i term is out_w(i), added by the caller
+        const int64_t ua = rowptr[u], ub = rowptr[u + 1];
+        if (sub == 0) {
+            r.eo += out_w[u];
+            r.ed += diag[u];
+        }
+        if (ub - ua <= ib - ia) {
+            // walk row u, look every entry up in ego(i)
+            for (int64_t q = ua + sub; q < ub; q += kLanes) {
+                const int32_t v = colidx[q];
+                bool in_ego = v == self;
+                if (!in_ego) {
+                    const int64_t p = find(colidx, ia, ib, v);
+                    in_ego = p < ib && colidx[p] == v;
+                }
+                if (in_ego) r.t += w ? w[q] : 1.0;
+            }
+        } else {
+            // walk ego(i) = row i (+ i itself when there is no self loop), look up in row u
+            for (int64_t q = ia + sub; q < ib; q += kLanes) {
+                const int32_t v = colidx[q];
+                const int64_t p = find(colidx, ua, ub, v);
+                if (p < ub && colidx[p] == v) r.t += w ? w[p] : 1.0;
+            }
+            if (!has_self && sub == 0) {
+                const int64_t p = find(colidx, ua, ub, self);
+                if (p < ub && colidx[p] == self) r.t += w ? w[p] : 1.0;
+            }
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void ego_finish(int64_t i, double t, double eo, double ed,
+                                           const double* __restrict__ out_w,
+                                           const double* __restrict__ diag, int directed,
+                                           double* __restrict__ internal,
+                                           double* __restrict__ external) {
+    const double T = out_w[i] + t;
+    internal[i] = directed ? T : (T + diag[i] + ed) * 0.5;
+    external[i] = out_w[i] + eo - T;
+}
+
+// rows shorter than kBigRow: one 8-lane group per row; longer rows are appended to big_rows
+__global__ void egonet_kernel(int64_t n, const int64_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                              const double* __restrict__ out_w, const double* __restrict__ diag,
+                              int directed, double* __restrict__ internal,
+                              double* __restrict__ external, int32_t* __restrict__ big_rows,
+                              int32_t* __restrict__ n_big) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = gid / kLanes;
+    const int sub = (int)(gid % kLanes);
+    EgoPartial r = {0.0, 0.0, 0.0};
+    bool mine = i < n;
+    if (mine && rowptr[i + 1] - rowptr[i] >= kBigRow) {
+        if (sub == 0) big_rows[atomicAdd(n_big, 1)] = (int32_t)i;
+        mine = false;
+    }
+    if (mine) r = ego_partial(i, sub, 0, 1, rowptr, colidx, w, out_w, diag);
+    const double t = group_sum(r.t, 0xffffffffu);
+    if (mine && sub == 0) ego_finish(i, t, r.eo, r.ed, out_w, diag, directed, internal, external);
+}
+
+// long rows: one 256-thread CTA (32 groups of 8 lanes) per row, fixed-order block reduction
+__global__ void __launch_bounds__(256)
+egonet_big_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                  const double* __restrict__ w, const double* __restrict__ out_w,
+                  const double* __restrict__ diag, int directed, double* __restrict__ internal,
+                  double* __restrict__ external, const int32_t* __restrict__ big_rows,
+                  const int32_t* __restrict__ n_big) {
+    __shared__ double part[3][256 / kLanes];
+    const int grp = threadIdx.x / kLanes, sub = threadIdx.x % kLanes;
+    const int count = *n_big;
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        const int64_t i = big_rows[idx];
+        const EgoPartial r = ego_partial(i, sub, grp, 256 / kLanes, rowptr, colidx, w, out_w, diag);
+        const double t = group_sum(r.t, 0xffffffffu);
+        __syncthreads();
+        if (sub == 0) {
+            part[0][grp] = t;
+            part[1][grp] = r.eo;
+            part[2][grp] = r.ed;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double st = 0.0, so = 0.0, sd = 0.0;
+            for (int g = 0; g < 256 / kLanes; ++g) {
+                st += part[0][g];
+                so += part[1][g];
+                sd += part[2][g];
+            }
+            ego_finish(i, st, so, sd, out_w, diag, directed, internal, external);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* rowptr_dev,
+                                      const int32_t* colidx_dev, const double* weights_dev,
+                                      int32_t directed, double* out_weight_dev,
+                                      double* in_weight_dev, double* diag_dev,
+                                      double* internal_dev, double* external_dev, int device,
+                                      void* stream) {
+    GR_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && nnz >= 0,
+               "gr_level0_features_f64: n = %lld, nnz = %lld", (long long)n, (long long)nnz);
+    if (n == 0) return GR_OK;
+    GR_REQUIRE(rowptr_dev != nullptr && (colidx_dev != nullptr || nnz == 0) && out_weight_dev != nullptr && diag_dev != nullptr &&
+               internal_dev != nullptr && external_dev != nullptr,
+               "gr_level0_features_f64: NULL argument");
+    GR_REQUIRE(!directed || in_weight_dev != nullptr,
+               "gr_level0_features_f64: a directed graph needs in_weight_dev");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "gr_level0_features_f64: cannot select device %d", device);
+    if (int rc = require_sm100(device)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* in_w = directed ? in_weight_dev : nullptr;
+    if (in_w) GR_CUDA_TRY(cudaMemsetAsync(in_w, 0, (size_t)n * sizeof(double), st));
+    const unsigned blocks = (unsigned)ceil_div<int64_t>(n * kLanes, 256);
+    row_stats_kernel<<<blocks, 256, 0, st>>>(n, rowptr_dev, colidx_dev, weights_dev,
+                                             out_weight_dev, in_w, diag_dev);
+    // rows of >= kBigRow arcs are collected by the first kernel and finished by the second
+    int32_t* big = nullptr;
+    GR_CUDA_TRY(cudaMallocAsync((void**)&big, (size_t)(nnz / kBigRow + 2) * sizeof(int32_t), st));
+    cudaMemsetAsync(big, 0, sizeof(int32_t), st);            // big[0] = counter, list from big + 1
+    egonet_kernel<<<blocks, 256, 0, st>>>(n, rowptr_dev, colidx_dev, weights_dev, out_weight_dev,
+                                          diag_dev, directed, internal_dev, external_dev, big + 1,
+                                          big);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    egonet_big_kernel<<<4 * sms, 256, 0, st>>>(rowptr_dev, colidx_dev, weights_dev, out_weight_dev,
+                                               diag_dev, directed, internal_dev, external_dev,
+                                               big + 1, big);
+    cudaFreeAsync(big, st);
+    count_launch(3);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(GR_ERR_CUDA, "level-0 kernels failed to launch: %s", cudaGetErrorString(e));
+    return GR_OK;
+}

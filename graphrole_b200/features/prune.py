@@ -88,12 +88,11 @@ class FeaturePruner:
         n_feat = len(names)
         if n_feat < 2:
             return []
-        binned = np.stack([vertical_log_binning(features[name].to_numpy()) for name in names])
+        gaps = self._binned_gaps(features)
         sets = _DisjointSets(n_feat)
         linked = np.zeros(n_feat, dtype=bool)
         for i in range(n_feat - 1):
-            gap = np.abs(binned[i + 1:] - binned[i]).max(axis=1)
-            for j in np.nonzero(gap <= self._feature_group_thresh)[0]:
+            for j in np.nonzero(gaps[i, i + 1:] <= self._feature_group_thresh)[0]:
                 sets.union(i, i + 1 + int(j))
                 linked[i] = linked[i + 1 + int(j)] = True
         groups: Dict[int, Set[Hashable]] = {}
@@ -101,6 +100,18 @@ class FeaturePruner:
             if linked[i]:
                 groups.setdefault(sets.find(i), set()).add(names[i])
         return list(groups.values())
+
+    def _binned_gaps(self, features: DataFrameLike) -> np.ndarray:
+        """[F, F] matrix of max-norm distances between the binned columns (host arithmetic;
+        DeviceFeaturePruner computes the same integers on the GPU)."""
+        names = list(features.columns)
+        binned = np.stack([vertical_log_binning(features[name].to_numpy()) for name in names])
+        gaps = np.zeros((len(names), len(names)), dtype=np.int64)
+        for i in range(len(names) - 1):
+            gap = np.abs(binned[i + 1:] - binned[i]).max(axis=1)
+            gaps[i, i + 1:] = gap
+            gaps[i + 1:, i] = gap
+        return gaps
 
     def _get_oldest_feature(self, feature_names: Set[Hashable]) -> Hashable:
         """Member generated in the earliest generation; ties broken by sorted name."""
@@ -114,3 +125,28 @@ class FeaturePruner:
     def _set_getitem(s: Set[Hashable]) -> Hashable:
         """Deterministic pick from a set: its smallest element."""
         return min(s)
+
+
+class DeviceFeaturePruner(FeaturePruner):
+    """FeaturePruner whose O(n) work -- binning every column and the pairwise max-norm
+    distances (prune.py:104-108) -- runs on the GPU (csrc/prune.cu through
+    gr_prune_bin_f64 / gr_prune_pairwise_gap_i32); grouping and the oldest-member choice stay
+    on the host.  Raises when the CUDA library or a device is missing."""
+
+    def __init__(self, generation_dict: Dict[int, DataFrameDict], feature_group_thresh: int,
+                 device=None) -> None:
+        super().__init__(generation_dict, feature_group_thresh)
+        self._device = device
+
+    def _binned_gaps(self, features: DataFrameLike) -> np.ndarray:
+        import torch
+        from graphrole_b200 import _native
+        device = torch.device(self._device if self._device is not None else 'cuda')
+        values = np.ascontiguousarray(features.to_numpy(dtype=np.float64))
+        pruner = _native.Pruner(values.shape[0], device)
+        try:
+            bins = pruner.bin_columns(torch.from_numpy(values).to(pruner.device))
+            gaps = pruner.pairwise_gaps(bins).cpu().numpy().astype(np.int64)
+        finally:
+            pruner.close()
+        return gaps

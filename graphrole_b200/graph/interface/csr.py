@@ -16,6 +16,7 @@ class CSRInterface(BaseGraphInterface):
         self.directed = G.directed
         self._set_attribute_kwargs(**kwargs)
         self._row_of = None
+        self._level0_frames = None
 
     def to_csr(self) -> CSRGraph:
         return self.G
@@ -37,8 +38,20 @@ class CSRInterface(BaseGraphInterface):
         cols = self.G.colidx[lo:hi].tolist()
         return cols if self.G.labels is None else [self.G.labels[c] for c in cols]
 
+    # A graph whose arrays already live in HBM gets its level-0 features from the GPU kernels
+    # (csrc/level0.cu); host-resident arrays use the scipy closed forms.  The choice follows
+    # where the caller put the data, it is not a fallback.
+    def _device_frames(self):
+        if self._level0_frames is None:
+            self._level0_frames = level0.device_feature_frames(self.G)
+        return self._level0_frames
+
     def _get_local_features(self) -> pd.DataFrame:
+        if self.G.rowptr.is_cuda:
+            return self._device_frames()[0]
         return level0.local_degree_features(self.G)
 
     def _get_egonet_features(self) -> pd.DataFrame:
+        if self.G.rowptr.is_cuda:
+            return self._device_frames()[1]
         return level0.egonet_features(self.G)

@@ -67,3 +67,37 @@ def egonet_features(g: CSRGraph) -> pd.DataFrame:
     return pd.DataFrame({'internal_edges': _maybe_int(internal, g.weights_integral),
                          'external_edges': _maybe_int(external, g.weights_integral)},
                         index=list(g.node_labels()))
+
+
+# ---- device path (csrc/level0.cu) -------------------------------------------------------------
+
+def device_features(g: CSRGraph, device=None):
+    """Level-0 columns computed on the GPU from the CSR arrays: ({column name: float64 CUDA
+    tensor [n]}, in the reference's column order).  Same closed forms as above, one
+    gr_level0_features_f64 call; the arrays are moved to `device` if they are not there yet."""
+    import torch
+    from graphrole_b200 import _native
+    if device is None:
+        device = g.rowptr.device if g.rowptr.is_cuda else torch.device('cuda')
+    device = torch.device(device)
+    weights = None if g.weights is None else g.weights.to(device)
+    out = _native.level0_features(g.rowptr.to(device), g.colidx.to(device), weights,
+                                  directed=g.directed)
+    if g.directed:
+        cols = {'in_degree': out['in_weight'], 'out_degree': out['out_weight'],
+                'total_degree': out['in_weight'] + out['out_weight']}
+    else:
+        cols = {'degree': out['out_weight'] + out['diag']}
+    cols['internal_edges'] = out['internal']
+    cols['external_edges'] = out['external']
+    return cols
+
+
+def device_feature_frames(g: CSRGraph, device=None):
+    """(local frame, egonet frame) like local_degree_features / egonet_features, computed by
+    device_features."""
+    cols = device_features(g, device)
+    index = list(g.node_labels())
+    host = {k: _maybe_int(v.cpu().numpy(), g.weights_integral) for k, v in cols.items()}
+    ego = {k: host.pop(k) for k in ('internal_edges', 'external_edges')}
+    return pd.DataFrame(host, index=index), pd.DataFrame(ego, index=index)

@@ -185,6 +185,54 @@ int gr_nmf_last_path(const gr_nmf_t* h);
 int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                      const float* W_dev, const float* H_dev, double* err_out, void* stream);
 
+/* ---- "next" rows of the path: what runs between the levels -------------
+ *
+ * Feature pruning, graphrole/features/prune.py.  The reference re-bins EVERY retained column
+ * after every level (features.apply(vertical_log_binning), prune.py:104) and compares all column
+ * pairs (pdist chebyshev, prune.py:107); connected components / oldest-member choice
+ * (prune.py:94-130) stay on the host (F <= ~10^2 columns).
+ *
+ * gr_prune_bin_f32 / _f64   vertical_log_binning (prune.py:13-56) of every column of X
+ *     [n_rows, d] (row stride ldx): bin 0 takes the lowest max(int(frac * n), 1) values plus
+ *     everything tied with the largest of them, bin 1 the same share of what is left, ...
+ *     Output is COLUMN-major: bins_dev[c * ldb + i] = bin of X[i, c] (ldb >= n_rows).
+ *     Integer results, bit-exact with the reference for inputs without NaN (the extractor
+ *     fills NaN with 0 first, extract.py:128-133); -0.0 and 0.0 tie like in np.unique.
+ *     frac outside (0, 1) is refused like prune.py:19-20.
+ * gr_prune_pairwise_gap_i32  gap_dev[i * d + j] = max_row |bins[i] - bins[j]| (Chebyshev
+ *     distance of binned columns; the reference links i and j when it is <= the level's
+ *     threshold, prune.py:108-111).  d <= 1024.  Exact.
+ * The handle owns the sort workspaces for n_rows rows (about 160 bytes per row).
+ */
+typedef struct gr_pruner gr_pruner_t;
+
+int gr_pruner_create(gr_pruner_t** out, int64_t n_rows, int device);
+int gr_pruner_destroy(gr_pruner_t* h);
+int gr_prune_bin_f32(gr_pruner_t* h, const float* X_dev, int64_t ldx, int32_t d, double frac,
+                     int32_t* bins_dev, int64_t ldb, void* stream);
+int gr_prune_bin_f64(gr_pruner_t* h, const double* X_dev, int64_t ldx, int32_t d, double frac,
+                     int32_t* bins_dev, int64_t ldb, void* stream);
+int gr_prune_pairwise_gap_i32(gr_pruner_t* h, const int32_t* bins_dev, int64_t ldb, int32_t d,
+                              int32_t* gap_dev, void* stream);
+
+/* Level-0 neighbourhood features from CSR arrays, replacing the per-node nx.ego_graph /
+ * nx.edge_boundary loop of graphrole/graph/interface/networkx.py:48-83 (igraph.py:61-103).
+ *   rowptr int64[n + 1], colidx int32[nnz] ascending and unique inside a row (out-neighbours),
+ *   weights fp64[nnz] or NULL (= 1 per arc); an undirected graph stores every edge as two arcs
+ *   and a self loop as one.
+ * Outputs, fp64[n] each (exact for integer weights):
+ *   out_weight  weighted out-degree                 in_weight  weighted in-degree (directed
+ *   diag        weight of the node's self loop                 only; NULL otherwise)
+ *   internal    `internal_edges`: weight inside the node's radius-1 (out-)egonet
+ *   external    `external_edges`: weight leaving that egonet
+ * Host composition (networkx.py:53-63): undirected `degree` = out_weight + diag (a self loop
+ * counts twice, like nx.Graph.degree); directed in/out/total_degree = in, out, in + out. */
+int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* rowptr_dev,
+                           const int32_t* colidx_dev, const double* weights_dev,
+                           int32_t directed, double* out_weight_dev, double* in_weight_dev,
+                           double* diag_dev, double* internal_dev, double* external_dev,
+                           int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
