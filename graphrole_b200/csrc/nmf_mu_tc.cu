@@ -27,6 +27,17 @@
 // P2(last) -- the epilogue of block i-1 overlaps P1(i) and the P1 ring keeps prefetching from
 // HBM during P2(i-1).
 //
+// Column-split CTA pairs (CL = 2, the default when f > 128): two CTAs of a thread-block cluster
+// work on the same 64-row block, each on half of the columns.  Every CTA then keeps only half of
+// H (32 KB instead of 64 KB at f = 512) and a block's X tiles are 64 KB per CTA, so the P1 ring
+// holds the whole next half-block while P2 of the previous one runs (with one CTA per block the
+// fourth P1 stage of every block was loaded on demand, ~2.2 us of HBM latency exposed per block,
+// and the two-slot P2 ring streamed the L2 re-reads at only 32 GB/s per SM -- timeline trace in
+// profiles/).  The price: X H^T is a sum over columns, so each CTA sends its partial [64, 32]
+// tile to the peer through distributed shared memory (st.shared::cluster + a remote mbarrier
+// arrive per row) and both CTAs do the (identical, fp32 addition is commutative) W update; rank
+// 0 stores W, the ranks alternate on W^T W, each rank stores its own columns of W^T X.
+//
 // What was measured on B200 while getting here (profiles/README.md, C5 = 10 M x 512, r = 32):
 //   * one in-order ring of 4 x 32 KB shared by both phases: 9.1 ms / iteration (both load
 //     latencies exposed every block);
@@ -61,17 +72,18 @@ constexpr int kStageABytes = kStageABoxes * kBoxBytes;      // 32 KB
 constexpr int kStageBytes = 2 * kBoxBytes;                  // 16 KB (P2 stage)
 constexpr int kHBoxBytes = kRP * kBoxCols * 4;              // 4 KB
 constexpr int kWnewBytes = kRP * kBlockRows * 4;            // 8 KB  (W_b^T, K-major: [role][row])
-constexpr int kMaxTiles = 11;                               // f <= 704 (TMEM columns)
 constexpr int kWSubBytes = 16 * kRP * 4;                    // 2 KB: one warp's 16 rows of a W tile
 constexpr int kMaxStagesA = 5, kMaxStagesB = 4;
 constexpr float kEps = 1.1920928955078125e-07f;
 
 // TMEM column map (512 columns allocated)
-constexpr int kColD1 = 0;      // 2 x 32: XHt double buffer (M=64 layout)
-constexpr int kColDen = 64;    // 2 x 32: W (H H^T) double buffer (M=64 layout)
-constexpr int kColWtW = 128;   // 32: W^T W (M=64 layout, rows 0..31 valid, 32..63 duplicates)
-constexpr int kColD2 = 160;    // tiles x 32: (W^T X)^T, M=64 layout per 64-column tile
+// NBUF = 2 (one CTA per block) or 3 (CTA pairs: the epilogue runs one block behind, see below)
+constexpr int kColD1 = 0;                                      // NBUF x 32: XHt (M=64 layout)
+__host__ __device__ constexpr int col_den(int nbuf) { return nbuf * kRP; }         // NBUF x 32: W (H H^T)
+__host__ __device__ constexpr int col_wtw(int nbuf) { return 2 * nbuf * kRP; }     // 32: W^T W (rows 0..31 valid)
+__host__ __device__ constexpr int col_d2(int nbuf) { return 2 * nbuf * kRP + kRP; }  // tiles x 32: (W^T X)^T
 constexpr int kTmemCols = 512;
+__host__ __device__ constexpr int max_tiles(int nbuf) { return (kTmemCols - col_d2(nbuf)) / kRP; }
 
 struct TcParams {
     int64_t n;
@@ -84,9 +96,9 @@ struct TcParams {
     float* part_wtx;     // [grid, 32, f]
     float* part_wtw;     // [grid, 32, r]
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
+    int cluster;         // CTAs per row block (1 or 2); must match the launch's cluster size
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
-                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs, 16 experiment: P1 reads
-                         // its K-major operand from tiles loaded with the 32-byte-atom swizzle
+                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -121,6 +133,59 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // 
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
+}
+// One lane of the (converged) warp.  ptxas knows a region guarded by elect.sync runs in exactly one
+// thread and emits tcgen05.mma there as a plain uniform instruction; under `lane == 0` it wraps
+// every MMA in an ELECT / BRA.U.ANY loop over the possibly-active lanes.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// ---- cluster helpers (CL = 2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 16-byte store into another CTA's shared memory whose bytes are counted on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, float c, float d,
+                                            uint32_t remote_bar) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+        ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                 ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y,
                                             uint32_t bar) {
@@ -159,6 +224,23 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// Same instruction with the two 64-bit shared-memory descriptors passed as 32-bit halves: the
+// high words are compile-time constants and the low words differ from a per-stage base by a
+// constant, so the issuing thread spends one add per operand per MMA.  (Building each descriptor
+// from scratch cost 17 SASS instructions and ~105 cycles per MMA -- 4x the tensor pipe's own
+// time for an M=64 N=32 K=8 tile -- and made the kernel MMA-issue-bound.)
+__device__ __forceinline__ void tc_mma_tf32_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                                  uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // 32 lanes x 32 columns of fp32: thread t of the warp gets lane (base + t), columns c..c+31
@@ -201,6 +283,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr & 0x3ffff) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
            ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
+// low word: start address and leading-dimension byte offset; high word: stride byte offset,
+// version, layout type
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) {
+    return ((addr & 0x3ffff) >> 4) | ((lbo >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo, uint64_t layout) {
+    return (sbo >> 4) | (1u << 14) | ((uint32_t)layout << 29);
+}
 // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit
 // 16 (1 = MN-major), N >> 3 [17,23), M >> 4 [24,29)
 constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
@@ -216,23 +306,26 @@ struct SmemLayout {
     uint32_t h;        // 4 * groups boxes of 4 KB
     uint32_t ring_a;   // P1 ring: stages of 32 KB
     uint32_t ring_b;   // P2 ring: stages of 16 KB
-    uint32_t wio;      // 2 x 8 KB: W_b tile in (TMA load, fp32, K-major SW128) / out (TMA store)
+    uint32_t wio;      // 2 (CL = 2: 3) x 8 KB: W_b tile in (TMA load, fp32, K-major SW128) / out (TMA store)
     uint32_t wnew;     // 8 KB: tf32(W_b new), [row][role] in the 32-byte-atom 128B swizzle
     uint32_t hht;      // 4 KB: H H^T as a K-major SW128 tile (TMA)
+    uint32_t xch;      // CL = 2: 3 x 8 KB, the peer's partial X H^T tiles land here
     uint32_t bars;     // mbarriers
     uint32_t tmem_ptr;
     uint32_t total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ring_b) {
+// groups = P1 stages per block handled by ONE CTA (ceil(all groups / cluster size))
+__host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ring_b, int cluster) {
     SmemLayout L;
     uint32_t off = 0;
     L.h = off;      off += (uint32_t)groups * kStageABoxes * kHBoxBytes;
     off = (off + 1023u) & ~1023u;
     L.ring_a = off; off += (uint32_t)ring_a * kStageABytes;
     L.ring_b = off; off += (uint32_t)ring_b * kStageBytes;
-    L.wio = off;    off += 2 * kWnewBytes;
+    L.wio = off;    off += (cluster > 1 ? 3 : 2) * kWnewBytes;
     L.wnew = off;   off += kWnewBytes;
     L.hht = off;    off += kHBoxBytes;
+    L.xch = off;    off += cluster > 1 ? 3 * kWnewBytes : 0;
     L.bars = off;   off += 64 * 8;
     L.tmem_ptr = off; off += 16;
     L.total = off;
@@ -240,8 +333,10 @@ __host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ri
 }
 // barrier slots
 enum { B_FULL_A = 0, B_EMPTY_A = 8, B_FULL_B = 16, B_EMPTY_B = 20, B_HFULL = 24, B_D1FULL = 25,
-       B_D1EMPTY = 27, B_WFULL = 29, B_WEMPTY = 30, B_D2FULL = 31, B_WINFULL = 32, B_COUNT = 34 };
+       B_D1EMPTY = 28, B_WFULL = 31, B_WEMPTY = 32, B_D2FULL = 33, B_WINFULL = 34, B_XCHFULL = 37,
+       B_COUNT = 40 };
 
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     const __grid_constant__ CUtensorMap map_x_mn,
@@ -252,7 +347,15 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     // 1024-byte alignment for the 128B swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemLayout L = smem_layout(p.groups, p.ring_a, p.ring_b);
+    // column split: this CTA handles P1 groups [g_lo, g_lo + G) = columns [col_lo, col_hi)
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int G0 = (p.groups + CL - 1) / CL;
+    const int g_lo = rank * G0;
+    const int G = min(G0, p.groups - g_lo);
+    const int col_lo = g_lo * kStageABoxes * kBoxCols;
+    const int col_hi = min(p.f, col_lo + G * kStageABoxes * kBoxCols);
+    const int T = (col_hi - col_lo + kTileCols - 1) / kTileCols;
+    const SmemLayout L = smem_layout(G0, p.ring_a, p.ring_b, CL);
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_h = s_base + L.h, s_ra = s_base + L.ring_a, s_rb = s_base + L.ring_b;
     const uint32_t s_wnew = s_base + L.wnew, s_wio = s_base + L.wio, s_hht = s_base + L.hht;
@@ -261,24 +364,32 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     auto bar = [&](int slot) { return s_bars + 8u * (uint32_t)slot; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = p.groups, T = p.tiles, NA = p.ring_a, NB = p.ring_b;
-    // blocks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int64_t nb = (p.n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int NA = p.ring_a, NB = p.ring_b;
+    // D1 / Den buffers and how many blocks P2 trails P1 in the MMA issue order.  With CTA pairs
+    // the epilogue is software-pipelined (the peer's partial needs ~1.5 us to cross the cluster),
+    // so block i's updated W exists one block later than with a single CTA.
+    constexpr int NBUF = CL > 1 ? 3 : 2, LAG = CL > 1 ? 2 : 1;   // W tile buffers: NBUF as well
+    constexpr int kColDen = col_den(NBUF), kColWtW = col_wtw(NBUF), kColD2 = col_d2(NBUF);
+    // row blocks of this CTA (pair): first, first + stride, ...
+    const int64_t first = blockIdx.x / CL, stride = gridDim.x / CL;
+    const int64_t nb = (p.n_blocks - first + stride - 1) / stride;
+    const uint32_t s_xch = s_base + L.xch;
 
     // ---- setup ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(bar(B_FULL_A + s), 1); mbar_init(bar(B_EMPTY_A + s), 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(bar(B_FULL_B + s), 1); mbar_init(bar(B_EMPTY_B + s), 1); }
         mbar_init(bar(B_HFULL), 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             mbar_init(bar(B_D1FULL + i), 1);
             mbar_init(bar(B_D1EMPTY + i), 4);
+            // CL = 2: one arrive.expect_tx per local epilogue warp + the peer's st.async bytes
+            mbar_init(bar(B_XCHFULL + i), 4);
         }
         mbar_init(bar(B_WFULL), 4);
         mbar_init(bar(B_WEMPTY), 1);
         mbar_init(bar(B_D2FULL), 1);
-        mbar_init(bar(B_WINFULL), 4);
-        mbar_init(bar(B_WINFULL + 1), 4);
+        for (int i = 0; i < 3; ++i) mbar_init(bar(B_WINFULL + i), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -289,18 +400,23 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_s;
+    // All 512 columns are allocated, so the allocation starts at lane 0 / column 0.  Using the
+    // constant lets the MMA thread form TMEM addresses in uniform registers; with the address
+    // loaded from shared memory every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST loop.
+    if (*tmem_ptr_s != 0) __trap();
+    constexpr uint32_t tmem = 0;
+    if (CL > 1) cluster_sync_all();      // the peer's barriers exist before anything arrives on them
 
     if (warp == 0) {
         // ================= TMA producer, P1 stream (HBM): H once, then 128-column stages =========
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(bar(B_HFULL), (uint32_t)(G * kStageABoxes + 1) * kHBoxBytes);
             for (int c = 0; c < G * kStageABoxes; ++c)
-                tma_load_2d(s_h + c * kHBoxBytes, &map_h, c * kBoxCols, 0, bar(B_HFULL));
+                tma_load_2d(s_h + c * kHBoxBytes, &map_h, col_lo + c * kBoxCols, 0, bar(B_HFULL));
             tma_load_2d(s_hht, &map_hht, 0, 0, bar(B_HFULL));
             uint32_t it = 0;
             for (int64_t i = 0; i < nb; ++i) {
-                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows);
+                const int row = (int)((first + i * stride) * kBlockRows);
                 GR_TRACE(0, i, 0);
                 for (int g = 0; g < G; ++g, ++it) {
                     const int st = it % NA;
@@ -309,17 +425,18 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     mbar_expect_tx(bar(B_FULL_A + st), kStageABytes);
                     for (int c = 0; c < kStageABoxes; ++c)
                         tma_load_2d(s_ra + st * kStageABytes + c * kBoxBytes,
-                                    (p.debug & 16) ? &map_x_mn : &map_x_k,
-                                    (g * kStageABoxes + c) * kBoxCols, row, bar(B_FULL_A + st));
+                                    &map_x_k,
+                                    col_lo + (g * kStageABoxes + c) * kBoxCols, row,
+                                    bar(B_FULL_A + st));
                 }
             }
         }
     } else if (warp == 6) {
         // ================= TMA producer, P2 stream (L2 re-reads, 32-byte-atom swizzle) ==========
-        if (lane == 0 && !(p.debug & 8)) {
+        if (!(p.debug & 8) && elect_one()) {
             uint32_t it = 0;
             for (int64_t i = 0; i < nb; ++i) {
-                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows);
+                const int row = (int)((first + i * stride) * kBlockRows);
                 for (int t = 0; t < T; ++t, ++it) {
                     const int st = it % NB;
                     mbar_wait(bar(B_EMPTY_B + st), ((it / NB) & 1) ^ 1);
@@ -327,13 +444,14 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     mbar_expect_tx(bar(B_FULL_B + st), kStageBytes);
                     for (int c = 0; c < 2; ++c)
                         tma_load_2d(s_rb + st * kStageBytes + c * kBoxBytes, &map_x_mn,
-                                    t * kTileCols + c * kBoxCols, row, bar(B_FULL_B + st));
+                                    col_lo + t * kTileCols + c * kBoxCols, row,
+                                    bar(B_FULL_B + st));
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_wait(bar(B_HFULL), 0);
             // Issue order: P1(0); then P1(i), P2(i-1) for i >= 1; finally P2(last).  Measured
             // alternatives (C5, r = 32): interleaving P2(i-1) stages into P1(i) 9.6 ms, polling
@@ -341,51 +459,54 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             // with 128 KB of ring space the slot turn-around bounds both streams, and blocking
             // mbarrier waits have less latency than a polling loop.
             uint32_t ita = 0, itb = 0;
-            for (int64_t i = 0; i <= nb; ++i) {
-                const bool do_p1 = i < nb, do_p2 = i >= 1;
-                const int buf1 = (int)(i & 1);
-                const int64_t j = i - 1;
+            for (int64_t i = 0; i < nb + LAG; ++i) {
+                const bool do_p1 = i < nb, do_p2 = i >= LAG;
+                const int buf1 = (int)(i % NBUF);        // D1 / Den buffer of block i
+                const int wbuf = buf1;                   // W tile buffer of block i
+                const int64_t j = i - LAG;
                 const uint32_t d1 = tmem + kColD1 + buf1 * kRP;
                 if (do_p1) {
                     // ---- P1(i): X_b . H^T into D1, 128 columns (16 k-steps) per stage
                     GR_TRACE(2, i, 0);
-                    mbar_wait(bar(B_D1EMPTY + buf1), (uint32_t)(((i >> 1) & 1) ^ 1));
+                    mbar_wait(bar(B_D1EMPTY + buf1), (uint32_t)(((i / NBUF) & 1) ^ 1));
                     tc_fence_after();
                     for (int g = 0; g < G; ++g, ++ita) {
                         const int st = ita % NA;
                         mbar_wait(bar(B_FULL_A + st), (ita / NA) & 1);
                         if (g == 0) GR_TRACE(2, i, 1);
                         tc_fence_after();
+                        if (!(p.debug & 1)) {
+                            const uint32_t a_lo = desc_lo(s_ra + st * kStageABytes, 16);
+                            const uint32_t b_lo = desc_lo(s_h + g * kStageABoxes * kHBoxBytes, 16);
+                            constexpr uint32_t hi = desc_hi(1024, kLayoutSw128);
 #pragma unroll
-                        for (int c = 0; c < kStageABoxes; ++c) {
-                            const uint32_t a0 = s_ra + st * kStageABytes + c * kBoxBytes;
-                            const uint32_t b0 = s_h + (g * kStageABoxes + c) * kHBoxBytes;
+                            for (int c = 0; c < kStageABoxes; ++c)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (!(p.debug & 1))
-                                tc_mma_tf32(d1, make_desc(a0 + k * 32, 16, 1024,
-                                                          (p.debug & 16) ? kLayoutSw128Base32
-                                                                         : kLayoutSw128),
-                                            make_desc(b0 + k * 32, 16, 1024, kLayoutSw128),
-                                            kIdescP1, (g | c | k) != 0);
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_tf32_split(d1, a_lo + (c * kBoxBytes + k * 32) / 16, hi,
+                                                      b_lo + (c * kHBoxBytes + k * 32) / 16, hi,
+                                                      kIdescP1, (uint32_t)(g | c | k));
                         }
                         tc_commit(bar(B_EMPTY_A + st));
                     }
                     // ---- P1'(i): Den = W_b . (H H^T) from the TMA-loaded W tile.  (Its load was
                     // issued after the epilogue of block i-2, which needed P2(i-3): already done.)
-                    mbar_wait(bar(B_WINFULL + buf1), (uint32_t)((i >> 1) & 1));
+                    mbar_wait(bar(B_WINFULL + wbuf), (uint32_t)((i / NBUF) & 1));
                     tc_fence_after();
+                    {
+                        const uint32_t a_lo = desc_lo(s_wio + wbuf * kWnewBytes, 16);
+                        const uint32_t b_lo = desc_lo(s_hht, 16);
+                        constexpr uint32_t hi = desc_hi(1024, kLayoutSw128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_tf32(tmem + kColDen + buf1 * kRP,
-                                    make_desc(s_wio + buf1 * kWnewBytes + k * 32, 16, 1024, kLayoutSw128),
-                                    make_desc(s_hht + k * 32, 16, 1024, kLayoutSw128), kIdescP1,
-                                    k != 0);
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_tf32_split(tmem + kColDen + buf1 * kRP, a_lo + k * 2, hi,
+                                              b_lo + k * 2, hi, kIdescP1, (uint32_t)k);
+                    }
                     tc_commit(bar(B_D1FULL + buf1));
                     GR_TRACE(2, i, 2);
                 }
                 if (do_p2) {
-                    // ---- P2(i-1): (W^T X)^T and W^T W with the updated W of block i-1
+                    // ---- P2(j), j = i - LAG: (W^T X)^T and W^T W with the updated W of block j
                     mbar_wait(bar(B_WFULL), (uint32_t)(j & 1));
                     GR_TRACE(2, j, 3);
                     tc_fence_after();
@@ -393,22 +514,31 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                         const int st = itb % NB;
                         if (!(p.debug & 8)) mbar_wait(bar(B_FULL_B + st), (itb / NB) & 1);
                         tc_fence_after();
-                        const uint32_t a0 = s_rb + st * kStageBytes;
+                        if (!(p.debug & 10)) {
+                            // k-step = 8 rows of the block = one 1 KB swizzle atom
+                            const uint32_t a_lo = desc_lo(s_rb + st * kStageBytes, kBoxBytes);
+                            const uint32_t b_lo = desc_lo(s_wnew, 0);
+                            constexpr uint32_t hi = desc_hi(512, kLayoutSw128Base32);
+                            const uint32_t acc0 = (uint32_t)(j != 0);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)   // k-step = 8 rows of the block
-                            if (!(p.debug & 10))
-                            tc_mma_tf32(tmem + kColD2 + t * kRP,
-                                        make_desc(a0 + k * 1024, kBoxBytes, 512, kLayoutSw128Base32),
-                                        make_desc(s_wnew + k * 1024, 0, 512, kLayoutSw128Base32),
-                                        kIdescP2, (j | k) != 0);
+                            for (int k = 0; k < 8; ++k)
+                                tc_mma_tf32_split(tmem + kColD2 + t * kRP, a_lo + k * 64, hi,
+                                                  b_lo + k * 64, hi, kIdescP2, acc0 | (uint32_t)k);
+                        }
                         tc_commit(bar(B_EMPTY_B + st));
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                    // W^T W: both CTAs of a pair hold the same W_b, so they take turns (block j goes
+                    // to rank j % 2) and the partials add up on the host side of the iteration
+                    if (CL == 1 || (int)(j & 1) == rank) {
                         // LBO = 0: the second 32-role group of "A" aliases the first (rows 32..63 of
                         // the accumulator duplicate rows 0..31 and are never read)
-                        const uint64_t d = make_desc(s_wnew + k * 1024, 0, 512, kLayoutSw128Base32);
-                        tc_mma_tf32(tmem + kColWtW, d, d, kIdescWtW, (j | k) != 0);
+                        const uint32_t d_lo = desc_lo(s_wnew, 0);
+                        constexpr uint32_t hi = desc_hi(512, kLayoutSw128Base32);
+                        const uint32_t acc0 = (uint32_t)(j >= CL);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            tc_mma_tf32_split(tmem + kColWtW, d_lo + k * 64, hi, d_lo + k * 64, hi,
+                                              kIdescWtW, acc0 | (uint32_t)k);
                     }
                     tc_commit(bar(B_WEMPTY));
                     GR_TRACE(2, j, 4);
@@ -425,76 +555,163 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         auto w_sub = [&](int buf) { return s_wio + buf * kWnewBytes + q * kWSubBytes; };
         auto load_w_sub = [&](int64_t i) {   // elected lane: TMA load of block i's sub-tile
             if (i >= nb) return;
-            const int buf = (int)(i & 1);
-            const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows) + q * 16;
+            const int buf = (int)(i % NBUF);
+            const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
             mbar_expect_tx(bar(B_WINFULL + buf), kWSubBytes);
             tma_load_2d(w_sub(buf), &map_w, 0, row, bar(B_WINFULL + buf));
         };
-        if (lane == 0) { load_w_sub(0); load_w_sub(1); }
+        if (lane == 0)
+            for (int b = 0; b < NBUF; ++b) load_w_sub(b);
         const int k = q * 16 + (lane & 15);              // row of the block held by this lane
-        for (int64_t i = 0; i < nb; ++i) {
-            const int buf = (int)(i & 1);
-            const uint32_t par = (uint32_t)((i >> 1) & 1);
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 0);
-            // ---- XHt and Den from TMEM (M=64 layout: row 16q + l in lane l < 16 of quarter q)
-            mbar_wait(bar(B_D1FULL + buf), par);
-            mbar_wait(bar(B_WINFULL + buf), par);        // the W tile the MMA already consumed
-            tc_fence_after();
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
-            float xht[32], den[32];
-            tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
-            tc_ld_32x32(tmem + lane_base + kColDen + buf * kRP, den);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
-            // ---- W row from the tile: [row][role], 16-byte chunk c at c ^ (row % 8)
-            unsigned char* wrow = smem + L.wio + buf * kWnewBytes + (uint32_t)k * 128;
-            float wn[32];
-            if (lane < 16) {
+        // The W update of one row once X H^T, the denominator and the old W row are in registers:
+        // writes the fp32 row back into the W tile (TMA store source); returns the new row in wn.
+        auto update_row = [&](const float (&xht)[32], const float (&den)[32], float (&wn)[32],
+                              unsigned char* wrow) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 t = *reinterpret_cast<const float4*>(wrow + ((c ^ (k & 7)) << 4));
-                    wn[4 * c] = t.x; wn[4 * c + 1] = t.y; wn[4 * c + 2] = t.z; wn[4 * c + 3] = t.w;
+            for (int c = 0; c < 8; ++c) {
+                const float4 t = *reinterpret_cast<const float4*>(wrow + ((c ^ (k & 7)) << 4));
+                wn[4 * c] = t.x; wn[4 * c + 1] = t.y; wn[4 * c + 2] = t.z; wn[4 * c + 3] = t.w;
+            }
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const float d = den[l] == 0.f ? kEps : den[l];
+                wn[l] = l < r ? wn[l] * __fdividef(xht[l], d) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(wrow + ((c ^ (k & 7)) << 4)) =
+                    make_float4(wn[4 * c], wn[4 * c + 1], wn[4 * c + 2], wn[4 * c + 3]);
+        };
+        // tf32 copy of the new row for P2 / W^T W: [row][role], 32-byte chunk c at c ^ (row % 4)
+        auto store_tf32_row = [&](const float (&wn)[32]) {
+            unsigned char* trow = smem + L.wnew + (uint32_t)k * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(trow + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4))) =
+                    make_float4(to_tf32(wn[4 * c]), to_tf32(wn[4 * c + 1]),
+                                to_tf32(wn[4 * c + 2]), to_tf32(wn[4 * c + 3]));
+        };
+        if constexpr (CL == 1) {
+            for (int64_t i = 0; i < nb; ++i) {
+                const int buf = (int)(i & 1);
+                const uint32_t par = (uint32_t)((i >> 1) & 1);
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 0);
+                // ---- XHt and Den from TMEM (M=64 layout: row 16q + l in lane l < 16 of quarter q)
+                mbar_wait(bar(B_D1FULL + buf), par);
+                mbar_wait(bar(B_WINFULL + buf), par);        // the W tile the MMA already consumed
+                tc_fence_after();
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
+                float xht[32], den[32], wn[32];
+                tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
+                tc_ld_32x32(tmem + lane_base + kColDen + buf * kRP, den);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
+                if (lane < 16)
+                    update_row(xht, den, wn, smem + L.wio + buf * kWnewBytes + (uint32_t)k * 128);
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
+                mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));   // P2(i-1) is done with wnew
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
+                if (lane < 16) store_tf32_row(wn);
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 5);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(B_WFULL));
+                    // ---- W tile out (rows beyond n / roles beyond r are clipped by the tensor
+                    // map), then reuse the buffer for block i + 2
+                    const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
+                    tma_store_2d(&map_w, 0, row, w_sub(buf));
+                    tma_store_commit_and_wait_read();
+                    load_w_sub(i + 2);
                 }
+                __syncwarp();
+                if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
+            }
+        } else {
+            // ---- CTA pair: X H^T is a sum over columns, each CTA holds the partial of its half.
+            // Software pipeline, iteration j:
+            //   (1) the peer's partial of block j-1 (sent one iteration ago) -> registers, re-arm
+            //       that exchange buffer for block j+2;
+            //   (2) own partial of block j: TMEM -> the peer's exchange buffer (st.async, the
+            //       bytes themselves complete the peer's mbarrier: one hop, no fence);
+            //   (3) W update of block j-1 from own partial + peer's partial (a + b == b + a bit
+            //       for bit, so both CTAs get the same W), tf32 copy, W tile store (rank 0).
+            // Step (1) precedes step (2) in program order, which is what makes three exchange
+            // buffers enough: the peer can only write block j+2 after it has used this CTA's
+            // partial of block j, sent in step (2).
+            const uint32_t peer = (uint32_t)(rank ^ 1);
+            if (lane == 0)
+                for (int b = 0; b < 3 && b < nb; ++b) mbar_expect_tx(bar(B_XCHFULL + b), kWSubBytes);
+            float pr[32];
+            for (int64_t jj = 0; jj <= nb; ++jj) {
+                const int64_t i = jj - 1;                    // block of steps (1) and (3)
+                if (q == 0 && lane == 0 && jj < nb) GR_TRACE(3, jj, 0);
+                if (i >= 0) {
+                    const int b = (int)(i % 3);
+                    mbar_wait_acquire_cluster(bar(B_XCHFULL + b), (uint32_t)((i / 3) & 1));
+                    if (lane < 16) {
+                        const unsigned char* prow = smem + L.xch + b * kWnewBytes + (uint32_t)k * 128;
 #pragma unroll
-                for (int l = 0; l < 32; ++l) {
-                    const float d = den[l] == 0.f ? kEps : den[l];
-                    wn[l] = l < r ? wn[l] * __fdividef(xht[l], d) : 0.f;
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 t = *reinterpret_cast<const float4*>(prow + ((c ^ (k & 7)) << 4));
+                            pr[4 * c] = t.x; pr[4 * c + 1] = t.y; pr[4 * c + 2] = t.z; pr[4 * c + 3] = t.w;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0 && i + 3 < nb) mbar_expect_tx(bar(B_XCHFULL + b), kWSubBytes);
                 }
-                // fp32 result back into the tile (TMA store source)
+                if (jj < nb) {
+                    const int b = (int)(jj % 3);
+                    mbar_wait(bar(B_D1FULL + b), (uint32_t)((jj / 3) & 1));
+                    tc_fence_after();
+                    if (q == 0 && lane == 0) GR_TRACE(3, jj, 1);
+                    float part[32];
+                    tc_ld_32x32(tmem + lane_base + kColD1 + b * kRP, part);
+                    if (lane < 16) {
+                        const uint32_t dst = mapa(s_xch + b * kWnewBytes + (uint32_t)k * 128, peer);
+                        const uint32_t rbar = mapa(bar(B_XCHFULL + b), peer);
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4*>(wrow + ((c ^ (k & 7)) << 4)) =
-                        make_float4(wn[4 * c], wn[4 * c + 1], wn[4 * c + 2], wn[4 * c + 3]);
-            }
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
-            // ---- tf32 copy for P2 / W^T W: [row][role], 32-byte chunk c at c ^ (row % 4).
-            // P2(i-1) must be done with that tile.
-            mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
-            if (lane < 16) {
-                unsigned char* trow = smem + L.wnew + (uint32_t)k * 128;
+                        for (int c = 0; c < 8; ++c)
+                            st_async_v4(dst + ((c ^ (k & 7)) << 4), part[4 * c], part[4 * c + 1],
+                                        part[4 * c + 2], part[4 * c + 3], rbar);
+                    }
+                    if (q == 0 && lane == 0) GR_TRACE(3, jj, 2);
+                }
+                if (i >= 0) {
+                    const int b = (int)(i % 3), wb = b;
+                    mbar_wait(bar(B_WINFULL + wb), (uint32_t)((i / 3) & 1));    // W tile of block i
+                    float xht[32], den[32], wn[32];
+                    tc_ld_32x32(tmem + lane_base + kColD1 + b * kRP, xht);
+                    tc_ld_32x32(tmem + lane_base + kColDen + b * kRP, den);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_D1EMPTY + b));
+                    if (lane < 16) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4*>(trow + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4))) =
-                        make_float4(to_tf32(wn[4 * c]), to_tf32(wn[4 * c + 1]),
-                                    to_tf32(wn[4 * c + 2]), to_tf32(wn[4 * c + 3]));
+                        for (int l = 0; l < 32; ++l) xht[l] += pr[l];
+                        update_row(xht, den, wn, smem + L.wio + wb * kWnewBytes + (uint32_t)k * 128);
+                    }
+                    if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
+                    mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));   // P2(i-1) is done with wnew
+                    if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
+                    if (lane < 16) store_tf32_row(wn);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar(B_WFULL));
+                        const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
+                        if (rank == 0) {
+                            tma_store_2d(&map_w, 0, row, w_sub(wb));
+                            tma_store_commit_and_wait_read();
+                        }
+                        load_w_sub(i + 3);
+                    }
+                    __syncwarp();
+                    if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
+                }
             }
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 5);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar(B_WFULL));
-                // ---- W tile out (rows beyond n / roles beyond r are clipped by the tensor map),
-                // then reuse the buffer for block i + 2
-                const int row = (int)((blockIdx.x + i * gridDim.x) * kBlockRows) + q * 16;
-                tma_store_2d(&map_w, 0, row, w_sub(buf));
-                tma_store_commit_and_wait_read();
-                load_w_sub(i + 2);
-            }
-            __syncwarp();
-            if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
@@ -504,15 +721,15 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         float v[32];
         for (int t = 0; t < T; ++t) {
             tc_ld_32x32(tmem + lane_base + kColD2 + t * kRP, v);
-            const int col = t * kTileCols + q * 16 + lane;   // M=64 layout: row 16q + l in lane l
-            if (lane < 16 && col < p.f)
+            const int col = col_lo + t * kTileCols + q * 16 + lane;   // M=64 layout: row 16q + l in lane l
+            if (lane < 16 && col < col_hi)
 #pragma unroll
                 for (int l = 0; l < 32; ++l)
                     if (l < r)
                         p.part_wtx[((int64_t)blockIdx.x * kRP + l) * p.f + col] = v[l];
         }
         tc_ld_32x32(tmem + lane_base + kColWtW, v);
-        if (q < 2 && lane < 16) {
+        if (nb > rank && q < 2 && lane < 16) {      // this CTA accumulated at least one block
             const int role = q * 16 + lane;   // M=64 layout
             if (role < r)
 #pragma unroll
@@ -523,6 +740,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     }
 
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // no remote store / arrive may target a CTA that has left
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -533,6 +751,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 // ---- host side ------------------------------------------------------------------------------------
 struct TcState {
     int grid = 0;
+    int cluster = 1;
     int ring_a = 0, ring_b = 0;
     size_t smem_bytes = 0;
     float* d_part_wtx = nullptr;
@@ -585,10 +804,22 @@ int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
 
 }  // namespace
 
+// CTAs per row block for f columns: 2 (column-split pair) when every CTA gets at least one
+// 128-column group and its tiles fit TMEM beside three D1 / Den buffers, else 1; 0 = the
+// accumulators do not fit TMEM at all.
+static int pick_cluster(int f) {
+    const int groups = ceil_div(f, kStageABoxes * kBoxCols);
+    const int cols_cta = ceil_div(groups, 2) * kStageABoxes * kBoxCols;
+    if (groups >= 2 && !getenv("GR_NMF_NO_CLUSTER") &&
+        ceil_div(std::min(f, cols_cta), kTileCols) <= max_tiles(3))
+        return 2;
+    return ceil_div(f, kTileCols) <= max_tiles(2) ? 1 : 0;
+}
+
 bool gr::nmf_tc_supported(const gr_nmf* h, const float* X, int64_t ldx) {
     if (getenv("GR_NMF_DISABLE_TC")) return false;
     return h->r <= kRP && h->r % 4 == 0 && h->f % 4 == 0 && ldx % 4 == 0 && aligned16(X) &&
-           ceil_div(h->f, kTileCols) <= kMaxTiles && h->n < ((int64_t)1 << 31) &&
+           pick_cluster(h->f) != 0 && h->n < ((int64_t)1 << 31) &&
            encode_fn() != nullptr;
 }
 
@@ -603,17 +834,23 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const int64_t n_blocks = ceil_div<int64_t>(h->n, kBlockRows);
-        s->grid = (int)std::min<int64_t>(sms, n_blocks);
+        // column-split CTA pairs need at least one 128-column group per CTA
+        s->cluster = pick_cluster(h->f);
+        s->grid = s->cluster * (int)std::min<int64_t>(sms / s->cluster, n_blocks);
+        const int groups_cta = ceil_div(groups, s->cluster);
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
-        // shared memory left after H goes to the rings: the P1 (HBM) ring first -- three 32 KB
-        // stages stream at > 6.5 TB/s (tools/exp_tma.cu) -- then the P2 (L2) ring
         auto fits = [&](int a, int b) {
-            return (size_t)smem_layout(groups, a, b).total + 1024 <= (size_t)max_smem;
+            return (size_t)smem_layout(groups_cta, a, b, s->cluster).total + 1024 <=
+                   (size_t)max_smem;
         };
-        // P1 (HBM) ring: three 32 KB stages; P2 (L2) ring: two 16 KB stages; anything left goes
-        // to the P2 ring first (its slots turn around faster)
-        s->ring_a = 3;
+        // One CTA per block: P1 (HBM) ring of three 32 KB stages (they stream at > 6.5 TB/s,
+        // tools/exp_tma.cu), P2 (L2) ring of two 16 KB stages, what is left goes to the P2 ring
+        // first (its slots turn around faster), then to the P1 ring.
+        // CTA pairs: a P1 ring of two stages already holds a whole half-block at f = 512, and
+        // a P2 ring that holds all four tiles of a half-block is worth more than a third P1
+        // stage (measured on C5: rings 2/4 5.2 ms, 3/2 6.4 ms per iteration).
+        s->ring_a = s->cluster == 2 ? 2 : 3;
         s->ring_b = 2;
         if (!fits(s->ring_a, s->ring_b)) s->ring_a = 2;
         if (!fits(s->ring_a, s->ring_b)) return fail(GR_ERR_CUDA, "nmf tc: shared memory budget");
@@ -624,12 +861,23 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
             s->ring_a = std::max(1, std::min(kMaxStagesA, atoi(getenv("GR_NMF_RING_A"))));
             s->ring_b = std::max(1, std::min(kMaxStagesB, atoi(getenv("GR_NMF_RING_B"))));
         }
-        s->smem_bytes = (size_t)smem_layout(groups, s->ring_a, s->ring_b).total + 1024;
-        GR_CUDA_TRY(cudaFuncSetAttribute(nmf_fused_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)s->smem_bytes));
-        GR_CUDA_TRY(cudaMalloc(&s->d_part_wtx, (size_t)s->grid * kRP * h->f * sizeof(float)));
-        GR_CUDA_TRY(cudaMalloc(&s->d_part_wtw, (size_t)s->grid * kRP * h->r * sizeof(float)));
+        s->smem_bytes = (size_t)smem_layout(groups_cta, s->ring_a, s->ring_b, s->cluster).total + 1024;
+        if (s->cluster == 2)
+            GR_CUDA_TRY(cudaFuncSetAttribute(nmf_fused_tc_kernel<2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)s->smem_bytes));
+        else
+            GR_CUDA_TRY(cudaFuncSetAttribute(nmf_fused_tc_kernel<1>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)s->smem_bytes));
+        const size_t wtx_bytes = (size_t)s->grid * kRP * h->f * sizeof(float);
+        const size_t wtw_bytes = (size_t)s->grid * kRP * h->r * sizeof(float);
+        GR_CUDA_TRY(cudaMalloc(&s->d_part_wtx, wtx_bytes));
+        GR_CUDA_TRY(cudaMalloc(&s->d_part_wtw, wtw_bytes));
+        // a CTA of a pair writes only its own columns of W^T X (and rank 0 alone W^T W): the
+        // rest of its partial block stays zero
+        GR_CUDA_TRY(cudaMemsetAsync(s->d_part_wtx, 0, wtx_bytes, st));
+        GR_CUDA_TRY(cudaMemsetAsync(s->d_part_wtw, 0, wtw_bytes, st));
     }
     if (s->X != X || s->ldx != ldx) {
         if (int rc = encode_2d(&s->map_x_k, X, (uint64_t)h->f, (uint64_t)h->n, (uint64_t)ldx * 4,
@@ -678,10 +926,26 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         p.trace = d_trace;
     }
     p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
-    nmf_fused_tc_kernel<<<s->grid, kThreads, s->smem_bytes, st>>>(
-        s->map_x_k, s->map_x_mn, s->map_h, s->map_hht, s->map_w, p);
+    p.cluster = s->cluster;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)s->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = s->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = s->cluster == 2
+        ? cudaLaunchKernelEx(&cfg, nmf_fused_tc_kernel<2>, s->map_x_k, s->map_x_mn, s->map_h,
+                             s->map_hht, s->map_w, p)
+        : cudaLaunchKernelEx(&cfg, nmf_fused_tc_kernel<1>, s->map_x_k, s->map_x_mn, s->map_h,
+                             s->map_hht, s->map_w, p);
     count_launch();
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess)
         return fail(GR_ERR_CUDA, "nmf_fused_tc_kernel launch failed: %s", cudaGetErrorString(e));
     if (p.trace) {

@@ -179,7 +179,7 @@ int gr_nmf_mu_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                   int32_t* n_iter_out, double* err_out, void* stream);
 /* 1 when the last gr_nmf_mu_f32 call on this handle ran the tcgen05 kernel, 0 for the FFMA
  * kernels (use_tf32 == 0, or a shape the tensor-core kernel does not take: it needs r <= 32,
- * f % 4 == 0, f <= 768, 16-byte aligned rows). */
+ * f % 4 == 0, f <= 1024, 16-byte aligned rows). */
 int gr_nmf_last_path(const gr_nmf_t* h);
 /* Frobenius error ||X - W H||_F (dense-residual form, _nmf.py:122), fp64 accumulation. */
 int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,

@@ -85,12 +85,14 @@ def test_against_oracle_and_live_sklearn_medium():
 
 
 def test_tensor_core_path_is_taken_and_matches_ffma():
-    """Shapes the tcgen05 kernel takes (r % 4 == 0, f % 4 == 0, f <= 704) must actually run it --
+    """Shapes the tcgen05 kernel takes (r % 4 == 0, f % 4 == 0, f <= 1024) must actually run it --
     no silent fallback -- and agree with the FFMA kernels; other shapes report 'ffma'."""
     rng = np.random.RandomState(3)
     for n, f, r, expect in [(3000, 512, 32, 'tcgen05'), (64 * 148 * 2 + 5, 128, 8, 'tcgen05'),
                             (1000, 96, 12, 'tcgen05'), (500, 704, 16, 'tcgen05'),
-                            (500, 768, 16, 'ffma'), (500, 64, 5, 'ffma'), (500, 30, 4, 'ffma')]:
+                            (500, 768, 16, 'tcgen05'), (9000, 1024, 32, 'tcgen05'),
+                            (700, 132, 4, 'tcgen05'), (64 * 74 * 3 + 1, 256, 32, 'tcgen05'),
+                            (500, 1028, 16, 'ffma'), (500, 64, 5, 'ffma'), (500, 30, 4, 'ffma')]:
         X = rng.rand(n, f)
         W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
         Wt, Ht, _, _ = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=5, tol=0, use_tf32=True)

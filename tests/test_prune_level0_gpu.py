@@ -85,7 +85,8 @@ def test_binning_large_column_properties():
     halving rule."""
     n = 2_000_000
     g = torch.Generator(device=DEV).manual_seed(1)
-    X = torch.stack([torch.rand(n, device=DEV, generator=g),
+    # column 0: all values distinct (a permutation); column 1: 50 distinct values
+    X = torch.stack([torch.randperm(n, device=DEV, generator=g).float() * 0.5,
                      torch.randint(0, 50, (n,), device=DEV, generator=g).float()], dim=1)
     p = _native.Pruner(n, DEV)
     bins = p.bin_columns(X)
@@ -251,3 +252,42 @@ def test_level0_device_hub_rows_and_frames():
     assert list(frame.columns) == ['degree', 'internal_edges', 'external_edges']
     assert frame['degree'].dtype == np.int64
     assert np.array_equal(frame['internal_edges'].values, (d + tri).astype(np.int64))
+
+
+# ---- device-resident recursion -------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', ['dangling', 'directed_weighted', 'undirected_weighted',
+                                  'karate', 'karate_weighted'])
+def test_device_resident_extractor_matches_reference_frames(refex_cases, name):
+    """Whole extract_features() with every O(n) step on the GPU (level 0, aggregation, binning,
+    pairwise gaps) against the frames the unmodified reference produced."""
+    from graphrole_b200.features.device import DeviceRecursiveFeatureExtractor
+    case = refex_cases[name]
+    G = graph_from_json(case['graph'])
+    rfe = DeviceRecursiveFeatureExtractor(_weighted_csr(G), device=DEV)
+    got = rfe.extract_features()
+    ref = frame_from_json(case['features'])
+    assert rfe.generation_count == case['generation_count']
+    assert list(got.columns) == list(ref.columns)
+    assert list(got.index) == list(ref.index)
+    np.testing.assert_allclose(got.values.astype(float), ref.values, rtol=1e-5, atol=1e-12)
+    if name == 'karate':
+        assert {str(k): sorted(v) for k, v in rfe._final_features.items()} == \
+            case['retained_by_generation']
+    # and identical (names, generation by generation) to the pandas-facing extractor
+    host = RecursiveFeatureExtractor(G)
+    host.extract_features()
+    assert {k: sorted(v) for k, v in host._final_features.items()} == \
+        {k: sorted(v) for k, v in rfe._final_features.items()}
+
+
+def test_device_resident_extractor_random_graph_equals_pandas_facing_extractor():
+    from graphrole_b200.features.device import DeviceRecursiveFeatureExtractor
+    G = nx.gnm_random_graph(2000, 9000, seed=11)
+    a = RecursiveFeatureExtractor(G).extract_features()
+    csr = interface.get_interface(G)(G).to_csr()
+    rfe = DeviceRecursiveFeatureExtractor(csr, device=DEV)
+    b = rfe.extract_features()
+    assert list(a.columns) == list(b.columns)
+    np.testing.assert_allclose(a.values.astype(float), b.values, rtol=1e-6)
+    assert set(rfe.timings_ms) >= {'level0', 'aggregate', 'bin', 'pairwise'}

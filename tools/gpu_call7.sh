@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/debug_nmf_tc.py > gpurun_out/nmf_pair_parity.log 2>&1; echo "parity rc=$?"
+cat gpurun_out/nmf_pair_parity.log | cut -c1-120 | tail -9
+timeout 300 python tools/bench_nmf.py --ranks 32 --iters 10 --paths tcgen05 2>&1 | cut -c1-200
+GR_NMF_TRACE=1 GR_NMF_TRACE_FIRST=20 timeout 300 python tools/bench_nmf.py --n 2000000 --ranks 32 --iters 1 --paths tcgen05 > gpurun_out/nmf_pair_trace.log 2>&1
+grep "^blk" gpurun_out/nmf_pair_trace.log | tail -8 | cut -c1-160
+GR_NMF_NO_CLUSTER=1 GR_NMF_TRACE=1 GR_NMF_TRACE_FIRST=20 timeout 300 python tools/bench_nmf.py --n 2000000 --ranks 32 --iters 1 --paths tcgen05 > gpurun_out/nmf_single_trace.log 2>&1
+grep "^blk" gpurun_out/nmf_single_trace.log | tail -8 | cut -c1-160
