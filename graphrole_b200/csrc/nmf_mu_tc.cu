@@ -65,11 +65,16 @@ constexpr int kThreads = 224;
 constexpr int kBlockRows = 64;      // rows of X per block (UMMA M of P1)
 constexpr int kRP = 32;             // roles padded (UMMA N)
 constexpr int kBoxCols = 32;        // 32 fp32 = 128 B = one swizzle row
-constexpr int kTileCols = 64;       // columns per P2 stage (UMMA M of P2)
+#ifndef GR_NMF_P2M
+#define GR_NMF_P2M 128
+#endif
+constexpr int kP2M = GR_NMF_P2M;    // UMMA M of P2 (64 or 128)
+constexpr int kTileCols = kP2M;     // columns per P2 stage
+constexpr int kStageBBoxes = kTileCols / kBoxCols;
 constexpr int kBoxBytes = kBlockRows * kBoxCols * 4;        // 8 KB
 constexpr int kStageABoxes = 4;                             // P1 stage: 128 columns
 constexpr int kStageABytes = kStageABoxes * kBoxBytes;      // 32 KB
-constexpr int kStageBytes = 2 * kBoxBytes;                  // 16 KB (P2 stage)
+constexpr int kStageBytes = kStageBBoxes * kBoxBytes;       // 16 / 32 KB (P2 stage)
 constexpr int kHBoxBytes = kRP * kBoxCols * 4;              // 4 KB
 constexpr int kWnewBytes = kRP * kBlockRows * 4;            // 8 KB  (W_b^T, K-major: [role][row])
 constexpr int kWSubBytes = 16 * kRP * 4;                    // 2 KB: one warp's 16 rows of a W tile
@@ -167,11 +172,10 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, f
                  ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // 16-byte store into another CTA's shared memory whose bytes are counted on that CTA's mbarrier
-__device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, float c, float d,
-                                            uint32_t remote_bar) {
+__device__ __forceinline__ void st_async_v2(uint32_t addr, float a, float b, uint32_t remote_bar) {
     asm volatile(
-        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-        ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+        ::"r"(addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
@@ -198,9 +202,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+__device__ __forceinline__ void tma_store_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// wait until at most `Pending` of this thread's bulk stores still have to read shared memory
+template <int Pending>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(Pending) : "memory");
 }
 // L2 prefetch of a whole tensor box (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
@@ -258,6 +266,22 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 lanes x 32 columns of fp32 spread over all 32 threads (shape .16x256b, 4 repeats): thread t
+// holds, for each 8-column group j = 0..3, v[4j + 0..1] = (lane t/4,     columns 8j + 2(t%4) + 0..1)
+//                                          v[4j + 2..3] = (lane t/4 + 8, columns 8j + 2(t%4) + 0..1)
+// -- the accumulator layout of an M=64 tile keeps its rows in lanes 0..15 of each lane quarter, so
+// with the 32x32b shape half of the warp would sit idle in the epilogue.
+__device__ __forceinline__ void tc_ld_16x32(uint32_t taddr, float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]),
+          "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]),
+          "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -298,7 +322,7 @@ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 constexpr uint32_t kIdescP1 = make_idesc(64, kRP, 0, 0);    // X K-major, H K-major
-constexpr uint32_t kIdescP2 = make_idesc(64, kRP, 1, 1);    // X^T MN-major, W_b MN-major
+constexpr uint32_t kIdescP2 = make_idesc(kP2M, kRP, 1, 1);    // X^T MN-major, W_b MN-major
 constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 1, 1);   // W_b MN-major on both sides
 
 // ---- shared memory carve-up ---------------------------------------------------------------------
@@ -442,7 +466,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     mbar_wait(bar(B_EMPTY_B + st), ((it / NB) & 1) ^ 1);
                     if (t < 8) GR_TRACE(1, i, t);
                     mbar_expect_tx(bar(B_FULL_B + st), kStageBytes);
-                    for (int c = 0; c < 2; ++c)
+                    for (int c = 0; c < kStageBBoxes; ++c)
                         tma_load_2d(s_rb + st * kStageBytes + c * kBoxBytes, &map_x_mn,
                                     col_lo + t * kTileCols + c * kBoxCols, row,
                                     bar(B_FULL_B + st));
@@ -562,69 +586,90 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         };
         if (lane == 0)
             for (int b = 0; b < NBUF; ++b) load_w_sub(b);
-        const int k = q * 16 + (lane & 15);              // row of the block held by this lane
-        // The W update of one row once X H^T, the denominator and the old W row are in registers:
-        // writes the fp32 row back into the W tile (TMA store source); returns the new row in wn.
-        auto update_row = [&](const float (&xht)[32], const float (&den)[32], float (&wn)[32],
-                              unsigned char* wrow) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 t = *reinterpret_cast<const float4*>(wrow + ((c ^ (k & 7)) << 4));
-                wn[4 * c] = t.x; wn[4 * c + 1] = t.y; wn[4 * c + 2] = t.z; wn[4 * c + 3] = t.w;
-            }
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const float d = den[l] == 0.f ? kEps : den[l];
-                wn[l] = l < r ? wn[l] * __fdividef(xht[l], d) : 0.f;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<float4*>(wrow + ((c ^ (k & 7)) << 4)) =
-                    make_float4(wn[4 * c], wn[4 * c + 1], wn[4 * c + 2], wn[4 * c + 3]);
+        // Fragment coordinates (tc_ld_16x32): this thread owns rows ra and ra + 8 of the block and,
+        // in every 8-column group j, the column pair 8j + cp, 8j + cp + 1.
+        const int ra = q * 16 + (lane >> 2), cp = 2 * (lane & 3);
+        // byte offset of (row k, even column c) in an fp32 [64][32] tile with the 128B swizzle
+        // (16-byte chunk c/4 at position (c/4) ^ (k % 8)) -- the W tiles and the exchange tiles
+        auto off_f32 = [](int k, int c) {
+            return (uint32_t)k * 128u + (uint32_t)((((c >> 2) ^ (k & 7)) << 4) | ((c & 3) << 2));
         };
-        // tf32 copy of the new row for P2 / W^T W: [row][role], 32-byte chunk c at c ^ (row % 4)
-        auto store_tf32_row = [&](const float (&wn)[32]) {
-            unsigned char* trow = smem + L.wnew + (uint32_t)k * 128;
+        // same for the tf32 copy read by P2 (32-byte chunk c/8 at position (c/8) ^ (k % 4))
+        auto off_tf32 = [](int k, int c) {
+            return (uint32_t)k * 128u + (uint32_t)((((c >> 3) ^ (k & 3)) << 5) | ((c & 7) << 2));
+        };
+        // W *= XHt / Den on this thread's 16 elements; the fp32 result goes back into the W tile
+        // (TMA store source) and stays in wn for the tf32 copy
+        auto update_w = [&](const float (&xht)[16], const float (&den)[16], float (&wn)[16],
+                            unsigned char* wtile) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<float4*>(trow + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4))) =
-                    make_float4(to_tf32(wn[4 * c]), to_tf32(wn[4 * c + 1]),
-                                to_tf32(wn[4 * c + 2]), to_tf32(wn[4 * c + 3]));
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ra + 8 * h, c = 8 * j + cp, e = 4 * j + 2 * h;
+                    float2* wp = reinterpret_cast<float2*>(wtile + off_f32(k, c));
+                    const float2 w = *wp;
+                    const float d0 = den[e] == 0.f ? kEps : den[e];
+                    const float d1 = den[e + 1] == 0.f ? kEps : den[e + 1];
+                    wn[e] = c < r ? w.x * __fdividef(xht[e], d0) : 0.f;
+                    wn[e + 1] = c + 1 < r ? w.y * __fdividef(xht[e + 1], d1) : 0.f;
+                    *wp = make_float2(wn[e], wn[e + 1]);
+                }
+        };
+        auto store_tf32 = [&](const float (&wn)[16]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ra + 8 * h, c = 8 * j + cp, e = 4 * j + 2 * h;
+                    *reinterpret_cast<float2*>(smem + L.wnew + off_tf32(k, c)) =
+                        make_float2(to_tf32(wn[e]), to_tf32(wn[e + 1]));
+                }
+        };
+        // W tile out (rows beyond n / roles beyond r are clipped by the tensor map), then refill a
+        // free tile buffer.  One CTA per block: two buffers, wait until this store has read its
+        // tile and load block i + 2 into it.  CTA pair: three buffers, so only the PREVIOUS
+        // block's store has to be done -- its buffer takes block i + 2 and the wait is off the
+        // epilogue's critical path.
+        auto store_w_and_refill = [&](int64_t i, int wb, bool do_store) {
+            const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
+            if (do_store) {
+                tma_store_2d(&map_w, 0, row, w_sub(wb));
+                tma_store_commit();
+                if constexpr (CL == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
+            if constexpr (CL == 1) load_w_sub(i + 2);
+            else if (i >= 1) load_w_sub(i + 2);
         };
         if constexpr (CL == 1) {
             for (int64_t i = 0; i < nb; ++i) {
                 const int buf = (int)(i & 1);
                 const uint32_t par = (uint32_t)((i >> 1) & 1);
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 0);
-                // ---- XHt and Den from TMEM (M=64 layout: row 16q + l in lane l < 16 of quarter q)
+                // ---- XHt and Den from TMEM (M=64 layout: rows 16q .. 16q+15 in lanes 0..15 of
+                // lane quarter q)
                 mbar_wait(bar(B_D1FULL + buf), par);
                 mbar_wait(bar(B_WINFULL + buf), par);        // the W tile the MMA already consumed
                 tc_fence_after();
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 1);
-                float xht[32], den[32], wn[32];
-                tc_ld_32x32(tmem + lane_base + kColD1 + buf * kRP, xht);
-                tc_ld_32x32(tmem + lane_base + kColDen + buf * kRP, den);
+                float xht[16], den[16], wn[16];
+                tc_ld_16x32(tmem + lane_base + kColD1 + buf * kRP, xht);
+                tc_ld_16x32(tmem + lane_base + kColDen + buf * kRP, den);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_D1EMPTY + buf));
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 2);
-                if (lane < 16)
-                    update_row(xht, den, wn, smem + L.wio + buf * kWnewBytes + (uint32_t)k * 128);
+                update_w(xht, den, wn, smem + L.wio + buf * kWnewBytes);
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
                 mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));   // P2(i-1) is done with wnew
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
-                if (lane < 16) store_tf32_row(wn);
+                store_tf32(wn);
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 5);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(bar(B_WFULL));
-                    // ---- W tile out (rows beyond n / roles beyond r are clipped by the tensor
-                    // map), then reuse the buffer for block i + 2
-                    const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
-                    tma_store_2d(&map_w, 0, row, w_sub(buf));
-                    tma_store_commit_and_wait_read();
-                    load_w_sub(i + 2);
+                    store_w_and_refill(i, buf, true);
                 }
                 __syncwarp();
                 if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
@@ -644,21 +689,23 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             const uint32_t peer = (uint32_t)(rank ^ 1);
             if (lane == 0)
                 for (int b = 0; b < 3 && b < nb; ++b) mbar_expect_tx(bar(B_XCHFULL + b), kWSubBytes);
-            float pr[32];
+            float pr[16];
             for (int64_t jj = 0; jj <= nb; ++jj) {
                 const int64_t i = jj - 1;                    // block of steps (1) and (3)
                 if (q == 0 && lane == 0 && jj < nb) GR_TRACE(3, jj, 0);
                 if (i >= 0) {
                     const int b = (int)(i % 3);
                     mbar_wait_acquire_cluster(bar(B_XCHFULL + b), (uint32_t)((i / 3) & 1));
-                    if (lane < 16) {
-                        const unsigned char* prow = smem + L.xch + b * kWnewBytes + (uint32_t)k * 128;
+                    const unsigned char* xt = smem + L.xch + b * kWnewBytes;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float4 t = *reinterpret_cast<const float4*>(prow + ((c ^ (k & 7)) << 4));
-                            pr[4 * c] = t.x; pr[4 * c + 1] = t.y; pr[4 * c + 2] = t.z; pr[4 * c + 3] = t.w;
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float2 t = *reinterpret_cast<const float2*>(
+                                xt + off_f32(ra + 8 * h, 8 * j + cp));
+                            pr[4 * j + 2 * h] = t.x;
+                            pr[4 * j + 2 * h + 1] = t.y;
                         }
-                    }
                     __syncwarp();
                     if (lane == 0 && i + 3 < nb) mbar_expect_tx(bar(B_XCHFULL + b), kWSubBytes);
                 }
@@ -667,46 +714,39 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     mbar_wait(bar(B_D1FULL + b), (uint32_t)((jj / 3) & 1));
                     tc_fence_after();
                     if (q == 0 && lane == 0) GR_TRACE(3, jj, 1);
-                    float part[32];
-                    tc_ld_32x32(tmem + lane_base + kColD1 + b * kRP, part);
-                    if (lane < 16) {
-                        const uint32_t dst = mapa(s_xch + b * kWnewBytes + (uint32_t)k * 128, peer);
-                        const uint32_t rbar = mapa(bar(B_XCHFULL + b), peer);
+                    float part[16];
+                    tc_ld_16x32(tmem + lane_base + kColD1 + b * kRP, part);
+                    const uint32_t dst = mapa(s_xch + b * kWnewBytes, peer);
+                    const uint32_t rbar = mapa(bar(B_XCHFULL + b), peer);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            st_async_v4(dst + ((c ^ (k & 7)) << 4), part[4 * c], part[4 * c + 1],
-                                        part[4 * c + 2], part[4 * c + 3], rbar);
-                    }
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            st_async_v2(dst + off_f32(ra + 8 * h, 8 * j + cp), part[4 * j + 2 * h],
+                                        part[4 * j + 2 * h + 1], rbar);
                     if (q == 0 && lane == 0) GR_TRACE(3, jj, 2);
                 }
                 if (i >= 0) {
                     const int b = (int)(i % 3), wb = b;
                     mbar_wait(bar(B_WINFULL + wb), (uint32_t)((i / 3) & 1));    // W tile of block i
-                    float xht[32], den[32], wn[32];
-                    tc_ld_32x32(tmem + lane_base + kColD1 + b * kRP, xht);
-                    tc_ld_32x32(tmem + lane_base + kColDen + b * kRP, den);
+                    float xht[16], den[16], wn[16];
+                    tc_ld_16x32(tmem + lane_base + kColD1 + b * kRP, xht);
+                    tc_ld_16x32(tmem + lane_base + kColDen + b * kRP, den);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(B_D1EMPTY + b));
-                    if (lane < 16) {
 #pragma unroll
-                        for (int l = 0; l < 32; ++l) xht[l] += pr[l];
-                        update_row(xht, den, wn, smem + L.wio + wb * kWnewBytes + (uint32_t)k * 128);
-                    }
+                    for (int l = 0; l < 16; ++l) xht[l] += pr[l];
+                    update_w(xht, den, wn, smem + L.wio + wb * kWnewBytes);
                     if (q == 0 && lane == 0) GR_TRACE(3, i, 3);
                     mbar_wait(bar(B_WEMPTY), (uint32_t)((i & 1) ^ 1));   // P2(i-1) is done with wnew
                     if (q == 0 && lane == 0) GR_TRACE(3, i, 4);
-                    if (lane < 16) store_tf32_row(wn);
+                    store_tf32(wn);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(bar(B_WFULL));
-                        const int row = (int)((first + i * stride) * kBlockRows) + q * 16;
-                        if (rank == 0) {
-                            tma_store_2d(&map_w, 0, row, w_sub(wb));
-                            tma_store_commit_and_wait_read();
-                        }
-                        load_w_sub(i + 3);
+                        store_w_and_refill(i, wb, rank == 0);
                     }
                     __syncwarp();
                     if (q == 0 && lane == 0) GR_TRACE(3, i, 6);
@@ -721,8 +761,9 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         float v[32];
         for (int t = 0; t < T; ++t) {
             tc_ld_32x32(tmem + lane_base + kColD2 + t * kRP, v);
-            const int col = col_lo + t * kTileCols + q * 16 + lane;   // M=64 layout: row 16q + l in lane l
-            if (lane < 16 && col < col_hi)
+            // M=64 layout: row 16q + l in lane l < 16 of quarter q; M=128: row 32q + l in lane l
+            const int col = col_lo + t * kTileCols + (kP2M == 64 ? q * 16 : q * 32) + lane;
+            if ((kP2M == 128 || lane < 16) && col < col_hi)
 #pragma unroll
                 for (int l = 0; l < 32; ++l)
                     if (l < r)
@@ -807,13 +848,18 @@ int encode_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
 // CTAs per row block for f columns: 2 (column-split pair) when every CTA gets at least one
 // 128-column group and its tiles fit TMEM beside three D1 / Den buffers, else 1; 0 = the
 // accumulators do not fit TMEM at all.
+constexpr size_t kSmemOptin = 232448;   // sm_100: 227 KB of dynamic shared memory per CTA
+static bool smem_fits(int groups_cta, int ring_a, int ring_b, int cluster) {
+    return (size_t)smem_layout(groups_cta, ring_a, ring_b, cluster).total + 1024 <= kSmemOptin;
+}
 static int pick_cluster(int f) {
     const int groups = ceil_div(f, kStageABoxes * kBoxCols);
     const int cols_cta = ceil_div(groups, 2) * kStageABoxes * kBoxCols;
     if (groups >= 2 && !getenv("GR_NMF_NO_CLUSTER") &&
-        ceil_div(std::min(f, cols_cta), kTileCols) <= max_tiles(3))
+        ceil_div(std::min(f, cols_cta), kTileCols) <= max_tiles(3) &&
+        smem_fits(ceil_div(groups, 2), 2, 1, 2))
         return 2;
-    return ceil_div(f, kTileCols) <= max_tiles(2) ? 1 : 0;
+    return ceil_div(f, kTileCols) <= max_tiles(2) && smem_fits(groups, 2, 1, 1) ? 1 : 0;
 }
 
 bool gr::nmf_tc_supported(const gr_nmf* h, const float* X, int64_t ldx) {
@@ -853,6 +899,7 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         s->ring_a = s->cluster == 2 ? 2 : 3;
         s->ring_b = 2;
         if (!fits(s->ring_a, s->ring_b)) s->ring_a = 2;
+        if (!fits(s->ring_a, s->ring_b)) s->ring_b = 1;
         if (!fits(s->ring_a, s->ring_b)) return fail(GR_ERR_CUDA, "nmf tc: shared memory budget");
         while (s->ring_b < kMaxStagesB && fits(s->ring_a, s->ring_b + 1)) ++s->ring_b;
         while (s->ring_a < kMaxStagesA && fits(s->ring_a + 1, s->ring_b)) ++s->ring_a;
