@@ -341,6 +341,13 @@ def run_gpu_arm(args):
                                   'sample': f'first {min(n, 1_000_000)} rows ({farcs} arcs), '
                                             f'{fdt:.2f} s'}}
 
+    # ---- the "next" rows of the path on the same graph (N = 1) ----------
+    if world == 1 and not args.no_next:
+        try:
+            line['next'] = next_rows_section(g, d, device)
+        except Exception as exc:
+            line['next'] = {'error': repr(exc)}
+
     # ---- hot path B beside it (N = 1): RolX NMF, BASELINE.json configs[4] ---------------------
     if world == 1 and not args.no_nmf:
         try:
@@ -354,6 +361,53 @@ def run_gpu_arm(args):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def next_rows_section(g, d, device):
+    """What runs around the aggregation in a whole extract_features(): level-0 features from the
+    CSR, vertical log binning of one level's [n, 2d] output, pairwise Chebyshev gaps of the binned
+    columns, and the whole device-resident recursion (pruning enabled, so the widths are the
+    data's own).  CUDA events, one warm-up call each."""
+    from graphrole_b200 import _native
+    from graphrole_b200.features.device import DeviceRecursiveFeatureExtractor
+    from graphrole_b200.graph import level0
+
+    def timed(fn, reps=1):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    ms = timed(lambda: level0.device_features(g))
+    out['level0'] = {'ms': ms, 'arcs_per_s': g.nnz / ms * 1e3,
+                     'columns': ['degree', 'internal_edges', 'external_edges']}
+    feats = g.handle(device).aggregate(torch.rand(g.n, d, device=device))
+    pruner = _native.Pruner(g.n, device)
+    bins = torch.empty((feats.shape[1], g.n), dtype=torch.int32, device=device)
+    ms = timed(lambda: pruner.bin_columns(feats, out=bins))
+    out['vertical_log_binning'] = {'columns': feats.shape[1], 'ms': ms,
+                                   'keys_per_s': feats.numel() / ms * 1e3}
+    ms = timed(lambda: pruner.pairwise_gaps(bins), reps=2)
+    f = bins.shape[0]
+    out['pairwise_gaps'] = {'columns': f, 'ms': ms,
+                            'pair_rows_per_s': f * (f - 1) / 2 * g.n / ms * 1e3}
+    pruner.close()
+    del feats, bins
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    rfe = DeviceRecursiveFeatureExtractor(g, device=device)
+    names, values = rfe.extract_features_device()
+    torch.cuda.synchronize()
+    out['extract_features_device_resident'] = {
+        'wall_s': time.perf_counter() - t0, 'generations': rfe.generation_count,
+        'features': len(names), 'kernel_ms': {k: round(v, 2) for k, v in rfe.timings_ms.items()}}
+    return out
 
 
 def nmf_section(device, n=10_000_000, f=512, ranks=(4, 8, 16, 32), iters=10):
@@ -412,6 +466,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-nmf', action='store_true')
+    ap.add_argument('--no-next', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':

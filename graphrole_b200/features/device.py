@@ -73,6 +73,9 @@ class DeviceRecursiveFeatureExtractor:
         self._names: List[str] = []                    # all retained columns, in frame order
         self._columns: Dict[str, torch.Tensor] = {}    # name -> fp32 [n]
         self._bins: Dict[str, torch.Tensor] = {}       # name -> int32 [n] (binning is per column)
+        # values of every feature ever recorded as retained: a later generation may prune it from
+        # the working set, the reference still reports it (its _final_features keeps the values)
+        self._final_values: Dict[str, torch.Tensor] = {}
         self._final_features: Dict[int, List[str]] = {}
         self.timings_ms: Dict[str, float] = {}
 
@@ -95,7 +98,7 @@ class DeviceRecursiveFeatureExtractor:
                     names.append(name)
         if not names:
             return names, torch.empty((self.graph.n, 0), device=self.device)
-        return names, torch.stack([self._columns[name] for name in names], dim=1)
+        return names, torch.stack([self._final_values[name] for name in names], dim=1)
 
     # ---- recursion -----------------------------------------------------------------------------
     def _run(self) -> None:
@@ -148,7 +151,11 @@ class DeviceRecursiveFeatureExtractor:
             self._names.remove(name)
             del self._columns[name], self._bins[name]
         # columns.difference(redundant): sorted unique names (extract.py:140)
-        self._final_features[self.generation_count] = sorted(set(names) - redundant)
+        # and pandas' Index.difference returns the names unsorted when nothing at all was dropped
+        retained = list(pd.Index(names).difference(list(redundant)))
+        self._final_features[self.generation_count] = retained
+        for name in retained:
+            self._final_values.setdefault(name, self._columns[name])
 
     # ---- timing --------------------------------------------------------------------------------
     class _Timer:

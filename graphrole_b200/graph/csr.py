@@ -61,8 +61,18 @@ class CSRGraph:
             raise ValueError('edge endpoint outside [0, n)')
         w = None if weights is None else np.asarray(weights, dtype=np.float64).ravel()
         if not directed:
-            loop = src == dst
-            src, dst = (np.concatenate([src, dst[~loop]]), np.concatenate([dst, src[~loop]]))
+            # an undirected edge is one object whichever way it is written: collapse repeats on
+            # the unordered pair first (last weight wins for BOTH directions), then mirror
+            lo, hi = np.minimum(src, dst), np.maximum(src, dst)
+            order = np.argsort(lo * np.int64(n) + hi, kind='stable')
+            pair = (lo * np.int64(n) + hi)[order]
+            last = np.ones(pair.size, dtype=bool)
+            last[:-1] = pair[1:] != pair[:-1]
+            lo, hi = lo[order][last], hi[order][last]
+            if w is not None:
+                w = w[order][last]
+            loop = lo == hi
+            src, dst = np.concatenate([lo, hi[~loop]]), np.concatenate([hi, lo[~loop]])
             if w is not None:
                 w = np.concatenate([w, w[~loop]])
         key = src * np.int64(n) + dst
