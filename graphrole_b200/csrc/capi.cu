@@ -7,6 +7,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "csr_handle.cuh"
 
 using namespace gr;
@@ -172,6 +174,8 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
     g->rowptr = rowptr_dev;
     g->colidx = colidx_dev;
 
+    if (const char* e = getenv("GR_REFEX_HUB_THRESHOLD")) g->hub_threshold = std::max(32, atoi(e));
+    if (const char* e = getenv("GR_REFEX_HUB_SEGMENT")) g->hub_segment = std::max(32, atoi(e));
     std::vector<int64_t> seg_begin, seg_end;
     g->h_hub_seg_first.push_back(0);
     for (int64_t r = 0; r < n_rows; ++r) {
@@ -186,11 +190,11 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
             return fail(GR_ERR_INVALID_GRAPH, "rows %lld..%lld hold more than 2^31 arcs",
                         (long long)std::max<int64_t>(r - 31, 0), (long long)r);
         }
-        if (e - b > kHubThreshold) {
+        if (e - b > g->hub_threshold) {
             g->h_hub_row.push_back(r);
-            for (int64_t s = b; s < e; s += kHubSegment) {
+            for (int64_t s = b; s < e; s += g->hub_segment) {
                 seg_begin.push_back(s);
-                seg_end.push_back(std::min(e, s + kHubSegment));
+                seg_end.push_back(std::min(e, s + g->hub_segment));
             }
             g->h_hub_seg_first.push_back((int64_t)seg_begin.size());
         }

@@ -10,6 +10,9 @@ namespace gr {
 // Rows with more arcs than kHubThreshold are not processed by a single warp: they are cut
 // into segments of kHubSegment arcs, each reduced by its own warp into an fp32 partial, and a
 // second kernel combines a row's partials in fp64 in segment order (deterministic, no atomics).
+// Defaults; GR_REFEX_HUB_THRESHOLD / GR_REFEX_HUB_SEGMENT override them when a handle is created
+// (the split is a property of the handle: every shard of a graph must be created with the same
+// values to reproduce the unsharded bits).
 constexpr int64_t kHubThreshold = 2048;
 constexpr int64_t kHubSegment = 1024;
 
@@ -30,6 +33,7 @@ struct gr_csr {
     int64_t n_hot_rows = 0;
 
     // hub decomposition (library-owned)
+    int64_t hub_threshold = gr::kHubThreshold, hub_segment = gr::kHubSegment;
     int64_t n_hub_rows = 0, n_segments = 0;
     std::vector<int64_t> h_hub_row;        // [n_hub_rows] row id, ascending
     std::vector<int64_t> h_hub_seg_first;  // [n_hub_rows + 1] first segment of each hub row

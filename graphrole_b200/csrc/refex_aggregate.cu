@@ -51,6 +51,7 @@ struct RefexArgs {
     float* __restrict__ partial;  // [n_segments, d], indexed by handle-global segment id
     int64_t n_seg_blocks;         // leading CTAs (blockIdx.x) that reduce hub segments
     int32_t rows_per_warp;
+    uint32_t hub_threshold;       // rows with more arcs are left to the segment warps
 };
 
 // Fused gather + broadcast (node-range sharded recursion): the mean rows are written into
@@ -249,7 +250,7 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
         const uint32_t beg = __shfl_sync(kFull, rp, r);
         const uint32_t end = __shfl_sync(kFull, rp, r + 1);
         const uint32_t deg = end - beg;
-        if (deg > (uint32_t)kHubThreshold) continue;  // segment warps + hub_fixup_kernel
+        if (deg > a.hub_threshold) continue;  // segment warps + hub_fixup_kernel
         float tot[VW];
         reduce_arcs<LPR, VW>(s, beg, end, xcol, a.ldx, col_ok, lane, pol_hot, tot);
         if (!col_ok) continue;
@@ -400,7 +401,15 @@ int aggregate_impl(gr_csr_t* g, const float* X, int64_t ldx, int32_t d, int64_t 
     a.seg_hi = seg_hi;
     a.partial = g->d_partial;
     a.n_seg_blocks = ceil_div<int64_t>(seg_hi - seg_lo, kWarps);
-    a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", 16, 1, 31);
+    // 16 consecutive rows per warp is the tuned point for ~40 arcs per row (C3).  A shard made of
+    // the heavy rows of a power-law graph (the first node range) would serialise up to
+    // 16 x hub_threshold arcs in one warp and its tail would outlast the rest of the launch
+    // (measured: 7.7 ms for a quarter of C3 instead of 4.4), so long-row handles get fewer rows
+    // per warp.  The grouping never changes the bits (chunking follows absolute arc positions).
+    const int64_t avg_deg = g->nnz / std::max<int64_t>(1, g->n_rows);
+    const int rpw_auto = avg_deg <= 64 ? 16 : (int)std::max<int64_t>(1, 1024 / avg_deg);
+    a.rows_per_warp = env_int("GR_REFEX_ROWS_PER_WARP", rpw_auto, 1, 31);
+    a.hub_threshold = (uint32_t)g->hub_threshold;
 
     bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) &&
                 (!out_sum || aligned16(out_sum)) && (!out_mean || aligned16(out_mean));

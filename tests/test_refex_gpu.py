@@ -351,6 +351,6 @@ def test_two_gpu_sharded_recursion_is_bit_identical():
     res = subprocess.run(
         [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
          '--master-addr', '127.0.0.1', '--master-port', '29731',
-         os.path.join(root, 'tools', 'check_sharded.py'), '--n', '200000', '--levels', '3'],
+         os.path.join(root, 'tools', 'check_sharded.py'), '--size', '200000', '--depth', '3'],
         capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and 'SHARDED CHECK OK' in res.stdout, res.stdout + res.stderr

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity check of the node-range sharded recursion (run under torchrun, one rank per
-GPU):  torchrun --nproc-per-node N tools/check_sharded.py [--n 300000] [--levels 4]
+GPU):  torchrun --nproc-per-node N tools/check_sharded.py [--size 300000] [--depth 4]
+(option names are chosen so that torchrun's own abbreviation matching cannot claim them)
 
 Every rank computes the unsharded recursion on its own GPU and compares, bit for bit, the rows
 it owns (sums and means) and the full replica of every level's input with what the sharded
@@ -19,10 +20,10 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=300_000)
-    ap.add_argument('--m', type=int, default=12)
-    ap.add_argument('--d', type=int, default=64)
-    ap.add_argument('--levels', type=int, default=4)
+    ap.add_argument('--size', dest='n', type=int, default=300_000)
+    ap.add_argument('--attach', dest='m', type=int, default=12)
+    ap.add_argument('--width', dest='d', type=int, default=64)
+    ap.add_argument('--depth', dest='levels', type=int, default=4)
     args = ap.parse_args()
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
