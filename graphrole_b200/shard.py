@@ -30,6 +30,53 @@ def nnz_balanced_ranges(rowptr: torch.Tensor, world: int) -> List[Tuple[int, int
     return [(bounds[i], bounds[i + 1]) for i in range(world)]
 
 
+def cost_balanced_ranges(rowptr: torch.Tensor, world: int, row_cost: float) -> List[Tuple[int, int]]:
+    """Contiguous row ranges that minimise the slowest rank when a rank's level time is
+    max(arcs gathered, row_cost * rows produced) -- the fused exchange: gathering an arc costs
+    d*4 bytes of HBM traffic, producing a row costs d*4 bytes of NVLink stores to each of the
+    world-1 peers, and the two overlap inside one kernel.  row_cost is the price of a row in
+    arcs: (HBM bandwidth / NVLink store bandwidth) * (world - 1).  Measured on C3 with
+    arc-balanced ranges the LAST rank (millions of low-degree rows) was bound by its stores:
+    4 GPUs 5.4 ms per level for 3.4 GB, 8 GPUs 7.0 ms for 4.2 GB, i.e. ~0.6 TB/s against
+    ~6.2 TB/s of gather traffic -- hence the default ratio of 10.
+    Binary search on the per-rank budget, greedy assignment from row 0; row_cost == 0 gives
+    (nearly) the arc-balanced ranges."""
+    n = rowptr.numel() - 1
+    if world == 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (world - 1)
+    rp = rowptr.detach().to('cpu')
+    nnz = int(rp[-1])
+    base = int(rp[0])
+
+    def assign(budget: float):
+        bounds, lo = [0], 0
+        for _ in range(world):
+            if lo >= n:
+                bounds.append(n)
+                continue
+            # furthest hi with arcs(lo, hi) <= budget and (hi - lo) * row_cost <= budget
+            hi_arcs = int(torch.searchsorted(rp, torch.tensor(int(rp[lo]) + int(budget)),
+                                             right=True)) - 1
+            hi_rows = n if row_cost <= 0 else lo + int(budget / row_cost)
+            hi = max(lo + 1, min(hi_arcs, hi_rows, n))       # always make progress
+            bounds.append(hi)
+            lo = hi
+        return bounds
+
+    lo_b, hi_b = 1.0, float(max(nnz - base, 1) + row_cost * n + 1)
+    for _ in range(60):
+        mid = 0.5 * (lo_b + hi_b)
+        if assign(mid)[-1] >= n:
+            hi_b = mid
+        else:
+            lo_b = mid
+        if hi_b - lo_b <= 1.0:
+            break
+    bounds = assign(hi_b)
+    bounds[-1] = n
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
 def exchange_rows(full: torch.Tensor, ranges: List[Tuple[int, int]], rank: int, group) -> None:
     """In-place all-gather of row slices: on entry rank g has filled full[lo_g:hi_g]; on exit
     every rank holds all rows.  `group` is the torch.distributed module/process group owner."""
@@ -136,15 +183,21 @@ class ShardedRefex:
                         for _ in range(2)]
             return
         import os
-        self.ranges = nnz_balanced_ranges(graph.rowptr, world)
+        exchange = exchange or os.environ.get('GR_SHARD_EXCHANGE', 'peer')
+        if exchange not in ('peer', 'nccl'):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        # fused exchange: a rank's stores to its world-1 peers overlap its gathers, so ranges
+        # balance max(arcs, row_cost * rows); the all-gather form balances arcs alone
+        ratio = float(os.environ.get('GR_SHARD_HBM_NVLINK_RATIO', '10'))
+        if exchange == 'peer' and ratio > 0 and os.environ.get('GR_SHARD_BALANCE', 'cost') == 'cost':
+            self.ranges = cost_balanced_ranges(graph.rowptr, world, ratio * (world - 1))
+        else:
+            self.ranges = nnz_balanced_ranges(graph.rowptr, world)
         lo, hi = self.ranges[rank]
         self.shard = graph.row_slice(lo, hi)
         self.handle = self.shard.handle(device)
         self.local_rows, self.local_nnz = hi - lo, self.shard.nnz
         self.sums = torch.empty((hi - lo, d), dtype=torch.float32, device=device)
-        exchange = exchange or os.environ.get('GR_SHARD_EXCHANGE', 'peer')
-        if exchange not in ('peer', 'nccl'):
-            raise ValueError("exchange must be 'peer' or 'nccl'")
         if exchange == 'peer':
             import torch.distributed as dist
             ok, why = 1, ''

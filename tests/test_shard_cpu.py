@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from graphrole_b200.graph.generators import barabasi_albert_csr, erdos_renyi_csr
-from graphrole_b200.shard import exchange_rows, nnz_balanced_ranges
+from graphrole_b200.shard import cost_balanced_ranges, exchange_rows, nnz_balanced_ranges
 from oracle import refex_oracle as oracle
 
 
@@ -24,6 +24,36 @@ def test_ranges_cover_all_rows_and_balance_arcs():
         arcs = [int(g.rowptr[hi] - g.rowptr[lo]) for lo, hi in ranges]
         assert sum(arcs) == g.nnz
         assert max(arcs) - min(arcs) <= 2 * int(g.out_degree().max())
+
+
+def test_cost_balanced_ranges_trade_arcs_for_rows():
+    """Fused exchange: a rank's time is max(arcs, row_cost * rows).  The ranges must cover all
+    rows, and their worst rank must beat the arc-balanced split under that cost."""
+    g = barabasi_albert_csr(200_000, 10, seed=1, device='cpu')
+    rp = g.rowptr
+
+    def worst(ranges, row_cost):
+        return max(max(int(rp[hi] - rp[lo]), row_cost * (hi - lo)) for lo, hi in ranges)
+
+    for world in (2, 4, 8):
+        row_cost = 10.0 * (world - 1)
+        ranges = cost_balanced_ranges(rp, world, row_cost)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == g.n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all(hi >= lo for lo, hi in ranges)
+        assert worst(ranges, row_cost) <= worst(nnz_balanced_ranges(rp, world), row_cost)
+        # within one row's worth of the continuous optimum's lower bound
+        lower = max(g.nnz / world, row_cost * g.n / world)
+        assert worst(ranges, row_cost) <= 1.35 * lower + int(g.out_degree().max())
+    # no row cost: the arc-balanced split (up to one row per boundary)
+    a = cost_balanced_ranges(rp, 4, 0.0)
+    b = nnz_balanced_ranges(rp, 4)
+    dmax = int(g.out_degree().max())
+    for (alo, ahi), (blo, bhi) in zip(a, b):
+        assert abs(int(rp[ahi] - rp[alo]) - int(rp[bhi] - rp[blo])) <= 2 * dmax
+    # degenerate inputs
+    assert cost_balanced_ranges(torch.zeros(5, dtype=torch.int64), 3, 20.0)[-1][1] == 4
+    assert cost_balanced_ranges(rp, 1, 0.0) == [(0, g.n)]
 
 
 def test_ranges_degenerate():
