@@ -1,42 +1,44 @@
 // Path B, tensor-core path: one fused pass over X per NMF multiplicative-update iteration,
 // hand-written for sm_100a with TMA (cp.async.bulk.tensor), mbarrier pipelines, tcgen05.mma
-// (kind::tf32, fp32 accumulation in TMEM) and tcgen05.ld epilogues.
+// (kind::tf32, fp32 accumulation in TMEM), tcgen05.ld epilogues and -- by default -- thread-block
+// clusters of two CTAs that exchange partial products through distributed shared memory.
 //
 // Per 64-row block b of X (persistent CTAs, one per SM, blocks round-robin):
 //   P1  XHt[64, 32]      = X_b (64 x f, K-major)  .  H^T      tcgen05.mma M=64  N=32 K=8 x f/8
 //   P1' Den[64, 32]      = W_b (64 x 32, K-major)  .  (H H^T)  tcgen05.mma M=64  N=32 K=8 x 4
-//   E   W_b             *= XHt / Den                         epilogue warps: tcgen05.ld, 32 fp32
-//                                                            ops per row; W_b tiles move by TMA
-//                                                            (load + store), tf32(W_b) -> smem
-//   P2  (W^T X)^T[f, 32] += X_b^T (MN-major)     .  W_b      tcgen05.mma M=64  N=32 K=8 x 8 per
-//                                                            64 columns; accumulators stay in TMEM
+//   E   W_b             *= XHt / Den                         epilogue warps: tcgen05.ld.16x256b (all
+//                                                            32 lanes hold data), 16 elements per
+//                                                            thread; W_b tiles move by TMA (load +
+//                                                            store), tf32(W_b) -> smem
+//   P2  (W^T X)^T[f, 32] += X_b^T (MN-major)     .  W_b      tcgen05.mma M=128 N=32 K=8 x 8 per
+//                                                            128 columns; accumulators stay in TMEM
 //       (W^T W)[32, 32]  += W_b^T                 .  W_b      tcgen05.mma M=64  N=32 K=8 x 8
 // The accumulators of P2 live in TMEM for the whole kernel and are written once per CTA as
 // partials; nmf_finish_iteration (nmf_mu.cu) reduces them in fixed order and updates H.
 //
 // X is read from HBM once per iteration: P2 re-loads the block's tiles through TMA a few
 // microseconds after P1 touched them, i.e. from L2 (126 MB), with the 32-byte-atom 128B swizzle
-// tcgen05 requires for MN-major tf32 operands; P1 uses the ordinary 128B swizzle (K-major).
-// Algorithmic bytes per iteration: n*f*4 + 2*n*r*4.
+// tcgen05 requires for MN-major tf32 operands; P1 uses the ordinary 128B swizzle (K-major; the
+// 32-byte-atom layout is refused for K-major operands, so one shared-memory copy cannot serve
+// both).  Algorithmic bytes per iteration: n*f*4 + 2*n*r*4.
 //
 // Warp roles (224 threads): warp 0 = TMA producer of the P1 stream (HBM), warp 1 = MMA issuer,
 // warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4), warp 6 = TMA producer of the P2
-// stream (L2 re-reads).  Each stream has its own shared-memory ring: P1 in 32 KB stages (four
-// 64 x 32 boxes = 128 columns under one mbarrier), P2 in 16 KB stages (two boxes = the 64
-// columns of one UMMA M tile).  MMA issue order: P1(0); then P1(i), P2(i-1) for i >= 1; finally
-// P2(last) -- the epilogue of block i-1 overlaps P1(i) and the P1 ring keeps prefetching from
-// HBM during P2(i-1).
+// stream (L2 re-reads).  Each stream has its own shared-memory ring of 32 KB stages (four
+// 64 x 32 boxes = 128 columns under one mbarrier).  MMA issue order: P1(i) then P2(i - LAG),
+// LAG = 1 with one CTA per block, 2 with CTA pairs -- the epilogue of the earlier block overlaps
+// P1(i) and the P1 ring keeps prefetching from HBM during P2.
 //
 // Column-split CTA pairs (CL = 2, the default when f > 128): two CTAs of a thread-block cluster
 // work on the same 64-row block, each on half of the columns.  Every CTA then keeps only half of
-// H (32 KB instead of 64 KB at f = 512) and a block's X tiles are 64 KB per CTA, so the P1 ring
-// holds the whole next half-block while P2 of the previous one runs (with one CTA per block the
-// fourth P1 stage of every block was loaded on demand, ~2.2 us of HBM latency exposed per block,
-// and the two-slot P2 ring streamed the L2 re-reads at only 32 GB/s per SM -- timeline trace in
-// profiles/).  The price: X H^T is a sum over columns, so each CTA sends its partial [64, 32]
-// tile to the peer through distributed shared memory (st.shared::cluster + a remote mbarrier
-// arrive per row) and both CTAs do the (identical, fp32 addition is commutative) W update; rank
-// 0 stores W, the ranks alternate on W^T W, each rank stores its own columns of W^T X.
+// H (32 KB instead of 64 KB at f = 512) and a block's X tiles are 64 KB per CTA, so each ring
+// holds a whole half-block ahead (with one CTA per block the fourth P1 stage of every block is
+// loaded on demand, ~2 us of HBM latency exposed per block -- timeline traces in profiles/).
+// The price: X H^T is a sum over columns, so each CTA sends its partial [64, 32] tile to the
+// peer through distributed shared memory: st.async stores whose bytes complete an mbarrier of
+// the peer (one hop, no fence), software-pipelined one block deep so the ~1.5 us hop is off the
+// critical path.  Both CTAs do the (identical, fp32 addition is commutative) W update; rank 0
+// stores W, the ranks alternate on W^T W, each rank stores its own columns of W^T X.
 //
 // What was measured on B200 while getting here (profiles/README.md, C5 = 10 M x 512, r = 32):
 //   * one in-order ring of 4 x 32 KB shared by both phases: 9.1 ms / iteration (both load
@@ -44,10 +46,15 @@
 //   * per-box (8 KB) mbarrier stages: a single-thread producer/consumer handshake costs ~500
 //     cycles, which caps a stream at ~4.4 TB/s regardless of ring depth; 32 KB per barrier
 //     streams at 6.6-7.4 TB/s with only 3 stages (tools/exp_tma.cu);
-//   * an epilogue that computes W (H H^T) per row on CUDA cores (1024 FMA + 32 IEEE divisions
-//     per thread, one warp per scheduler) takes ~10 us per block and bounds the kernel
-//     (timeline trace, GR_NMF_TRACE); the r x r product therefore also runs on the tensor
-//     core (P1'), W tiles are moved by TMA, and the epilogue is ~250 instructions per row.
+//   * an epilogue that computes W (H H^T) per row on CUDA cores takes ~10 us per block; the
+//     r x r product therefore also runs on the tensor core (P1') and W tiles move by TMA;
+//   * tcgen05.mma issued under `if (lane == 0)` compiles to an ELECT / BRA loop plus 17
+//     instructions of descriptor arithmetic, ~105 cycles per MMA: the kernel was issue-bound at
+//     8.45 ms; elect.sync + per-stage descriptors with constant increments -> 6.3 ms;
+//   * an M=64 N=32 K=8 TF32 MMA costs ~50 cycles of tensor pipe, M=128 ~76: 128-column P2 tiles;
+//   * 64 remote mbarrier arrives per block serialise (~1.5 us), a cluster-scope fence in front of
+//     one arrive per warp is worse (10.3 ms); interleaving P2's accumulators k-outer doubles
+//     P2's time; final: 4.3 - 4.9 ms per iteration (r = 4 .. 32), tensor-pipe bound.
 
 #include <cuda.h>
 
@@ -130,15 +137,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
 // One lane of the (converged) warp.  ptxas knows a region guarded by elect.sync runs in exactly one
 // thread and emits tcgen05.mma there as a plain uniform instruction; under `lane == 0` it wraps
 // every MMA in an ELECT / BRA.U.ANY loop over the possibly-active lanes.
@@ -167,19 +165,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};"
-                 ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// 16-byte store into another CTA's shared memory whose bytes are counted on that CTA's mbarrier
+// 8-byte store into another CTA's shared memory whose bytes are counted on that CTA's mbarrier
 __device__ __forceinline__ void st_async_v2(uint32_t addr, float a, float b, uint32_t remote_bar) {
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
         ::"r"(addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
-                 ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -210,11 +200,6 @@ template <int Pending>
 __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(Pending) : "memory");
 }
-// L2 prefetch of a whole tensor box (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                 ::"l"(map), "r"(x), "r"(y) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -224,15 +209,6 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
 }
 // Same instruction with the two 64-bit shared-memory descriptors passed as 32-bit halves: the
 // high words are compile-time constants and the low words differ from a per-stage base by a
@@ -302,11 +278,6 @@ __device__ __forceinline__ float to_tf32(float x) {
 // shared-memory matrix descriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46),
 // version = 1 [46,48), layout type [61,64)
 constexpr uint64_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo,
-                                              uint64_t layout) {
-    return (uint64_t)((addr & 0x3ffff) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
-           ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
-}
 // low word: start address and leading-dimension byte offset; high word: stride byte offset,
 // version, layout type
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) {
