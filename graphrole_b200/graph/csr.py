@@ -130,6 +130,58 @@ class CSRGraph:
         torch.cumsum(counts, 0, out=rowptr[1:])
         return cls(rowptr, colidx, directed=directed)
 
+    # ---- wire formats (the reference has none: graph objects only) ---
+    def save(self, path: str) -> None:
+        """Write the arrays (and labels / weights when present) as one .npz file."""
+        rp, ci = self.host_arrays()
+        arrays = {'rowptr': rp, 'colidx': ci, 'directed': np.array(self.directed),
+                  'n_cols': np.array(self.n_cols),
+                  'weights_integral': np.array(self.weights_integral)}
+        if self.weights is not None:
+            arrays['weights'] = self.weights.cpu().numpy()
+        if self.labels is not None:
+            arrays['labels'] = np.asarray(self.labels)
+        np.savez(path, **arrays)
+
+    @classmethod
+    def load(cls, path: str, device=None) -> 'CSRGraph':
+        """Read a file written by save(); `device` moves the arrays there."""
+        with np.load(path, allow_pickle=False) as z:
+            labels = z['labels'].tolist() if 'labels' in z.files else None
+            g = cls(z['rowptr'], z['colidx'], labels=labels, directed=bool(z['directed']),
+                    weights=z['weights'] if 'weights' in z.files else None,
+                    weights_integral=bool(z['weights_integral']))
+            g.n_cols = int(z['n_cols'])
+        if device is not None:
+            moved = g.to(device)
+            if g.weights is not None:
+                moved.weights = g.weights.to(device)
+            g = moved
+        return g
+
+    @classmethod
+    def from_edge_list_file(cls, path: str, directed: bool = False, weighted: bool = False,
+                            comment: str = '#', delimiter: Optional[str] = None) -> 'CSRGraph':
+        """Text edge list, one `u v [w]` per line (whitespace or `delimiter` separated, lines
+        starting with `comment` skipped).  Node tokens become labels; rows are numbered in
+        sorted-label order (integers sort numerically), like every other ingest path."""
+        import pandas as pd
+        cols = [0, 1, 2] if weighted else [0, 1]
+        sep = delimiter if delimiter is not None else r'\s+'
+        frame = pd.read_csv(path, sep=sep, comment=comment, header=None, usecols=cols,
+                            engine='python' if delimiter is None else 'c', dtype={0: str, 1: str})
+        u, v = frame[0].to_numpy(), frame[1].to_numpy()
+        try:
+            u, v = u.astype(np.int64), v.astype(np.int64)
+        except ValueError:
+            pass
+        labels, inverse = np.unique(np.concatenate([u, v]), return_inverse=True)
+        src, dst = inverse[:u.size], inverse[u.size:]
+        w = frame[2].to_numpy(dtype=np.float64) if weighted else None
+        integral = bool(w is None or np.all(w == np.round(w)))
+        return cls.from_edges(src, dst, n=labels.size, directed=directed, weights=w,
+                              labels=labels.tolist(), weights_integral=integral)
+
     # ---- queries mirroring the plugin API ---------------------------------------------
     def node_labels(self):
         return self.labels if self.labels is not None else range(self.n)

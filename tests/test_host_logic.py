@@ -110,6 +110,49 @@ def test_csr_from_edges_symmetrises_and_dedupes():
         CSRGraph.from_edges([0], [9], n=3)
 
 
+def test_csr_from_edges_undirected_repeats_keep_the_last_weight_both_ways():
+    """Re-adding an undirected edge the other way round replaces its weight for both
+    directions (what nx.Graph.add_edge does)."""
+    g = CSRGraph.from_edges([0, 1, 2], [1, 0, 2], n=3, weights=[5.0, 7.0, 2.0])
+    rp, ci = g.host_arrays()
+    assert rp.tolist() == [0, 1, 2, 3] and ci.tolist() == [1, 0, 2]
+    assert g.weights.tolist() == [7.0, 7.0, 2.0]
+    G = nx.Graph()
+    G.add_edge(0, 1, weight=5.0)
+    G.add_edge(1, 0, weight=7.0)
+    assert G[0][1]['weight'] == 7.0
+
+
+def test_csr_save_load_and_edge_list_file(tmp_path):
+    g = CSRGraph.from_edges([0, 0, 3], [1, 2, 3], n=4, weights=[1.5, 2.0, 4.0],
+                            labels=['a', 'b', 'c', 'd'], weights_integral=False)
+    path = str(tmp_path / 'g.npz')
+    g.save(path)
+    h = CSRGraph.load(path)
+    assert h.labels == g.labels and h.directed == g.directed and h.n_cols == g.n_cols
+    assert torch_equal(h.rowptr, g.rowptr) and torch_equal(h.colidx, g.colidx)
+    assert torch_equal(h.weights, g.weights) and h.weights_integral is False
+    # text edge list: integer labels sort numerically, comments are skipped
+    txt = tmp_path / 'edges.txt'
+    txt.write_text('# u v w\n10 2 1.0\n2 7 3.0\n10 7 2.0\n')
+    e = CSRGraph.from_edge_list_file(str(txt), weighted=True)
+    assert e.labels == [2, 7, 10] and e.n == 3 and e.nnz == 6
+    G = nx.Graph()
+    G.add_weighted_edges_from([(10, 2, 1.0), (2, 7, 3.0), (10, 7, 2.0)])
+    a = interface.CSRInterface(e).get_neighborhood_features()
+    b = interface.NetworkxInterface(G).get_neighborhood_features()
+    pd.testing.assert_frame_equal(a.astype(float), b.astype(float))
+    named = tmp_path / 'named.csv'
+    named.write_text('x,y\ny,z\n')
+    d = CSRGraph.from_edge_list_file(str(named), directed=True, delimiter=',')
+    assert d.labels == ['x', 'y', 'z'] and d.nnz == 2 and d.directed
+
+
+def torch_equal(a, b):
+    import torch
+    return torch.equal(a, b)
+
+
 @pytest.mark.parametrize('name', ['path4', 'dangling', 'directed_weighted', 'undirected_weighted',
                                   'karate', 'karate_weighted', 'attributes'])
 def test_level0_features_match_reference(refex_cases, name):
