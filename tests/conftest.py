@@ -53,3 +53,11 @@ def prune_cases():
 def roles_cases():
     with open(os.path.join(GOLDEN, 'roles_cases.json')) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope='session')
+def prune_reference_tables():
+    """The reference's own known-answer tables for the pruner (tests/test_features/
+    test_prune.py), re-run through the unmodified reference by tests/golden/make_golden.py."""
+    with open(os.path.join(GOLDEN, 'prune_reference_tables.json')) as f:
+        return json.load(f)

@@ -16,6 +16,7 @@ Outputs (all small, committed):
   refex_random.npz     seeded random graphs with injected float feature matrices and the
                        reference's `_get_next_features` output for them
   prune_cases.json     reference pruner outputs (binning vectors, dropped sets) on seeded data
+  prune_reference_tables.json  the reference's own known-answer tables for the pruner, re-run
   nmf_cases.npz        sklearn MU runs with explicit (W0, H0): factors after a fixed number
                        of iterations and at the stopping iteration, plus
                        graphrole.roles.factor.get_nmf_decomposition under np.random.seed
@@ -248,6 +249,47 @@ def prune_cases():
         json.dump(cases, f)
 
 
+def prune_reference_tables():
+    """The inputs of the reference's own known-answer tables for the pruning step
+    (tests/test_features/test_prune.py:17-99 vertical_log_binning, :119-153 prune_features,
+    :155-185 _group_features), re-run through the unmodified reference: pins our restatements
+    to exactly the cases the reference pins itself on."""
+    r10 = np.arange(10)
+    binning_inputs = {
+        'empty': ([], 0.5), 'single 0': ([0], 0.5), 'single nonzero': ([1], 0.5),
+        'repeated': ([1, 1], 0.5), '2 bins': ([1, 2], 0.5),
+        '2 bins with repeated lower bin': ([1, 2, 1], 0.5),
+        '2 bins with repeated upper bin': ([1, 2, 2], 0.5),
+        'negative and zeros': ([-1, 0, 0], 0.5), '1 through 4': ([1, 2, 3, 4], 0.5),
+        '1 through 5': ([1, 2, 3, 4, 5], 0.5), '1 through 6': ([1, 2, 3, 4, 5, 6], 0.5),
+        'range(10)': (r10.tolist(), 0.5), '-range(10)': ((-1 * r10).tolist(), 0.5),
+        'non-integer': ((-0.1 * r10).tolist(), 0.5), 'frac=0.1': (r10.tolist(), 0.1),
+        'frac=0.25': (r10.tolist(), 0.25),
+    }
+    out = {'binning': [], 'prune': [], 'group': []}
+    for name, (arr, frac) in binning_inputs.items():
+        binned = vertical_log_binning(np.array(arr), frac=frac)
+        out['binning'].append({'name': name, 'arr': arr, 'frac': frac,
+                               'binned': np.asarray(binned).tolist()})
+    feats = pd.DataFrame({'a': [1, 2, 3, 10], 'b': [1, 2, 3, 1], 'c': [2, 1, 1, 4],
+                          'd': [1, 1, 1, 1], 'e': [1, 1, 2, 0]})
+    gen_dict = {0: {'a': {}, 'b': {}, 'c': {}}, 1: {'d': {}, 'e': {}}}
+    for thresh in (0, 1, 2):
+        dropped = FeaturePruner(gen_dict, thresh).prune_features(feats)
+        out['prune'].append({'values': feats.values.tolist(), 'columns': list(feats.columns),
+                             'generations': {str(k): sorted(v) for k, v in gen_dict.items()},
+                             'thresh': thresh, 'dropped': sorted(dropped)})
+    feats = pd.DataFrame({'a': [1, 2, 3], 'b': [1, 2, 3], 'c': [2, 1, 1], 'd': [1, 1, 1]})
+    gen_dict = {0: {'b': {}, 'a': {}}, 1: {'c': {}, 'd': {}}}
+    for thresh in (0, 1, 2, -1):
+        groups = FeaturePruner(gen_dict, thresh)._group_features(feats)
+        out['group'].append({'values': feats.values.tolist(), 'columns': list(feats.columns),
+                             'thresh': thresh,
+                             'groups': sorted(sorted(g) for g in groups)})
+    with open(os.path.join(HERE, 'prune_reference_tables.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+
+
 def nmf_cases():
     """sklearn (the third-party owner of path B's arithmetic; installed 1.9.0) with shared init.
 
@@ -316,6 +358,7 @@ if __name__ == '__main__':
     refex_cases()
     refex_random()
     prune_cases()
+    prune_reference_tables()
     nmf_cases()
     roles_cases()
     print('golden fixtures written to', HERE)

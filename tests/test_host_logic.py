@@ -213,6 +213,25 @@ def test_prune_features_golden(prune_cases):
         assert sorted(got) == case['dropped']
 
 
+def test_pruner_on_the_references_own_tables(prune_reference_tables):
+    """Host pruner against every case of the reference's known-answer tables
+    (tests/test_features/test_prune.py:17-99, 119-153, 155-185)."""
+    t = prune_reference_tables
+    for case in t['binning']:
+        for arr in (np.array(case['arr']), pd.Series(case['arr'], dtype=float)):
+            assert vertical_log_binning(arr, case['frac']).tolist() == case['binned'], case['name']
+    for case in t['prune']:
+        feats = pd.DataFrame(case['values'], columns=case['columns'])
+        gens = {int(k): {name: {} for name in v} for k, v in case['generations'].items()}
+        got = FeaturePruner(gens, case['thresh']).prune_features(feats)
+        assert sorted(got) == case['dropped']
+    for case in t['group']:
+        feats = pd.DataFrame(case['values'], columns=case['columns'])
+        groups = FeaturePruner({0: {'b': {}, 'a': {}}, 1: {'c': {}, 'd': {}}},
+                               case['thresh'])._group_features(feats)
+        assert sorted(sorted(g) for g in groups) == case['groups']
+
+
 def test_oldest_feature_tie_break():
     pruner = FeaturePruner({0: {'b': {}, 'a': {}}, 1: {'c': {}}}, 0)
     assert pruner._get_oldest_feature({'c', 'b', 'a'}) == 'a'

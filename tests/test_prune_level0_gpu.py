@@ -48,6 +48,28 @@ def test_binning_matches_reference_vectors(prune_cases, dtype):
     assert _native.launch_count() > launches
 
 
+def test_device_pruner_on_the_references_own_tables(prune_reference_tables):
+    """GPU binning / grouping against the reference's known-answer tables
+    (tests/test_features/test_prune.py:17-99, 119-153, 155-185); the empty vector never reaches
+    the device (a feature matrix has at least one row)."""
+    t = prune_reference_tables
+    for case in t['binning']:
+        if not case['arr']:
+            continue
+        got = _bins(np.array(case['arr'], dtype=np.float64), case['frac'])[0]
+        assert got.tolist() == case['binned'], case['name']
+    for case in t['prune']:
+        feats = pd.DataFrame(case['values'], columns=case['columns'])
+        gens = {int(k): {name: {} for name in v} for k, v in case['generations'].items()}
+        got = DeviceFeaturePruner(gens, case['thresh']).prune_features(feats)
+        assert sorted(got) == case['dropped']
+    for case in t['group']:
+        feats = pd.DataFrame(case['values'], columns=case['columns'])
+        groups = DeviceFeaturePruner({0: {'b': {}, 'a': {}}, 1: {'c': {}, 'd': {}}},
+                                     case['thresh'])._group_features(feats)
+        assert sorted(sorted(g) for g in groups) == case['groups']
+
+
 @pytest.mark.parametrize('n', [1, 2, 3, 31, 32, 33, 1000, 4097])
 @pytest.mark.parametrize('frac', [0.5, 0.3, 0.9, 0.05])
 def test_binning_small_sizes_heavy_ties(n, frac):
