@@ -148,6 +148,26 @@ def refex_cases():
                                           for n, d in G.nodes(data=True)},
                            'level0': frame_to_json(lvl0), 'next': frame_to_json(nxt)}
 
+    # (8) the graphs of the reference's own interface tests (tests/test_graph/
+    # test_interface.py:50-67: 7 nodes, 7 edges, weights, node attributes); the level-0 tables
+    # the reference asserts there (:124-148, :150-186, :188-220) are what these frames hold
+    edges = [(0, 1), (0, 2), (0, 3), (3, 6), (4, 5), (4, 6), (5, 6)]
+    weights = [2, 1.5, 3, 0.25, 0.75, 2.5, 1]
+    G = nx.Graph()
+    G.add_nodes_from(range(7))
+    G.add_edges_from(edges)
+    lvl0 = RecursiveFeatureExtractor(G, aggs=AGGS).graph.get_neighborhood_features()
+    assert lvl0['internal_edges'].tolist() == [3, 1, 1, 2, 3, 3, 4]          # :133-138
+    assert lvl0['external_edges'].tolist() == [1, 2, 2, 4, 1, 1, 1]          # :139-144
+    cases['iface_undirected'] = {'graph': graph_to_json(G), 'level0': frame_to_json(lvl0)}
+    G = nx.DiGraph()
+    G.add_nodes_from(range(7))
+    G.add_weighted_edges_from([(u, v, w) for (u, v), w in zip(edges, weights)])
+    lvl0 = RecursiveFeatureExtractor(G, aggs=AGGS).graph.get_neighborhood_features()
+    assert lvl0['internal_edges'].tolist() == [6.5, 0, 0, 0.25, 4.25, 1, 0]  # :172-177
+    assert lvl0['external_edges'].tolist() == [0.25, 0, 0, 0, 0, 0, 0]       # :178-183
+    cases['iface_directed_weighted'] = {'graph': graph_to_json(G), 'level0': frame_to_json(lvl0)}
+
     with open(os.path.join(HERE, 'refex_cases.json'), 'w') as f:
         json.dump(cases, f, indent=1)
 

@@ -154,7 +154,8 @@ def torch_equal(a, b):
 
 
 @pytest.mark.parametrize('name', ['path4', 'dangling', 'directed_weighted', 'undirected_weighted',
-                                  'karate', 'karate_weighted', 'attributes'])
+                                  'karate', 'karate_weighted', 'attributes', 'iface_undirected',
+                                  'iface_directed_weighted'])
 def test_level0_features_match_reference(refex_cases, name):
     case = refex_cases[name]
     G = graph_from_json(case['graph'], case.get('node_attrs'))

@@ -207,7 +207,8 @@ def test_device_pruner_equals_host_pruner_on_extractor_frames():
 # ---- level-0 features -------------------------------------------------------------------------------
 
 @pytest.mark.parametrize('name', ['path4', 'dangling', 'directed_weighted', 'undirected_weighted',
-                                  'karate', 'karate_weighted'])
+                                  'karate', 'karate_weighted', 'iface_undirected',
+                                  'iface_directed_weighted'])
 def test_level0_device_matches_reference_tables(refex_cases, name):
     case = refex_cases[name]
     G = graph_from_json(case['graph'])
