@@ -90,7 +90,9 @@ def _worker(rank, world, port, levels, equal_rows, ret):
         g = barabasi_albert_csr(3000, 6, seed=3, device='cpu')
         d = 5
         X0 = torch.rand(g.n, d, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
-        if equal_rows:
+        if equal_rows == 'cost':       # the fused exchange's split: max(arcs, row cost) balanced
+            ranges = cost_balanced_ranges(g.rowptr, world, 10.0 * (world - 1))
+        elif equal_rows:
             ranges = [(k * g.n // world, (k + 1) * g.n // world) for k in range(world)]
         else:
             ranges = nnz_balanced_ranges(g.rowptr, world)
@@ -110,9 +112,9 @@ def _worker(rank, world, port, levels, equal_rows, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('equal_rows', [False, True])
+@pytest.mark.parametrize('equal_rows', [False, True, 'cost'])
 def test_two_rank_recursion_equals_single_process(equal_rows):
-    world, levels = 2, 3
+    world, levels = (3, 3) if equal_rows == 'cost' else (2, 3)
     port = _free_port()
     manager = mp.Manager()
     ret = manager.dict()
