@@ -110,7 +110,7 @@ struct TcParams {
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
     int cluster;         // CTAs per row block (1 or 2); must match the launch's cluster size
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
-                         // 4 skip epilogue math, 8 skip P2 TMA loads + MMAs
+                         // 8 skip P2 TMA loads + MMAs (results are then meaningless: timing only)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
