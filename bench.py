@@ -281,7 +281,7 @@ def run_gpu_arm(args):
                    'l2': 'inputs larger than L2 (feature matrix %.2f GB vs 126 MB L2)'
                          % (n * d * 4 / 1e9),
                    'parallelism': 'single GPU' if world == 1 else
-                   f'node-range sharded x{world}, nnz-balanced ranges, full input replica per GPU',
+                   f'node-range sharded x{world}, {engine.balance}, full input replica per GPU',
                    'exchange': {'none': 'none (single GPU)',
                                 'peer': 'fused: gather kernel stores mean rows into every '
                                         'replica over NVLink-mapped peer pointers + flag barrier',

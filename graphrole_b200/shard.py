@@ -175,6 +175,7 @@ class ShardedRefex:
         self.exchange_note = ''
         self.peers = None
         device = graph.rowptr.device
+        self.balance = 'single range'
         if world == 1:
             self.ranges = [(0, graph.n)]
             self.handle = graph.handle(device)
@@ -190,8 +191,10 @@ class ShardedRefex:
         # balance max(arcs, row_cost * rows); the all-gather form balances arcs alone
         ratio = float(os.environ.get('GR_SHARD_HBM_NVLINK_RATIO', '10'))
         if exchange == 'peer' and ratio > 0 and os.environ.get('GR_SHARD_BALANCE', 'cost') == 'cost':
+            self.balance = f'max(arcs, {ratio * (world - 1):g} x rows)-balanced ranges'
             self.ranges = cost_balanced_ranges(graph.rowptr, world, ratio * (world - 1))
         else:
+            self.balance = 'arc-balanced ranges'
             self.ranges = nnz_balanced_ranges(graph.rowptr, world)
         lo, hi = self.ranges[rank]
         self.shard = graph.row_slice(lo, hi)
