@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from graphrole_b200.features.prune import DeviceFeaturePruner, FeaturePruner
+from graphrole_b200.features.prune import DeviceFeaturePruner
 from graphrole_b200.graph import interface
 from graphrole_b200.types import DataFrameDict, DataFrameLike
 
@@ -53,6 +53,11 @@ class RecursiveFeatureExtractor:
         pd.DataFrame.sum,
         pd.DataFrame.mean,
     ]
+
+    # The O(n) part of pruning (binning + pairwise distances, prune.py:104-108) runs on the GPU;
+    # like the aggregation it raises when there is no CUDA device -- there is no silent host
+    # path.  (Unit tests of the host-side bookkeeping inject the NumPy FeaturePruner here.)
+    pruner_class = DeviceFeaturePruner
 
     def __init__(
         self,
@@ -143,11 +148,7 @@ class RecursiveFeatureExtractor:
     def _update(self, features: DataFrameLike) -> None:
         """Merge a generation's candidate features, prune, and record what was retained."""
         merged = pd.concat([self._features, features], axis=1, sort=True).fillna(0)
-        # the O(n) part of pruning (binning + pairwise distances) runs on the GPU whenever the
-        # process has one -- extract_features() cannot run without it anyway; the host class
-        # only serves GPU-less unit tests of the bookkeeping
-        pruner_cls = DeviceFeaturePruner if torch.cuda.is_available() else FeaturePruner
-        pruner = pruner_cls(self._final_features, self._feature_group_thresh)
+        pruner = self.pruner_class(self._final_features, self._feature_group_thresh)
         redundant = pruner.prune_features(merged)
         self._features = merged.drop(columns=redundant)
         retained = features.columns.difference(redundant)

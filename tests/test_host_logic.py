@@ -254,6 +254,7 @@ def _seeded_rfe():
 def test_update_prunes_and_records_retained():
     """Behaviour of tests/test_features/test_extract.py:124-159."""
     rfe = _seeded_rfe()
+    rfe.pruner_class = FeaturePruner     # bookkeeping under test; the GPU pruner has its own tests
     existing = rfe._features
     rng = np.random.RandomState(0)
     new = pd.concat([
