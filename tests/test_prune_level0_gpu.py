@@ -102,6 +102,22 @@ def test_binning_many_columns_strided_input(d):
         assert np.array_equal(got[c], prune_oracle.vertical_log_binning(Xh[:, c]))
 
 
+def test_binning_300k_rows_equals_the_oracle_exactly():
+    """A size the definitional oracle still finishes in seconds: every bin of every row."""
+    n = 300_000
+    rng = np.random.RandomState(9)
+    g = barabasi_albert_csr(n, 6, seed=9, device=DEV)
+    deg = g.out_degree().double().cpu().numpy()              # power-law ties
+    X = np.stack([rng.rand(n), rng.randint(0, 7, n).astype(float), deg,
+                  np.round(rng.randn(n), 1)], axis=1)
+    for dtype in (np.float64, np.float32):
+        Xd = X.astype(dtype)
+        got = _bins(Xd)
+        for c in range(X.shape[1]):
+            want = prune_oracle.vertical_log_binning(Xd[:, c].astype(np.float64))
+            assert np.array_equal(got[c], want), (dtype, c)
+
+
 def test_binning_large_column_properties():
     """2 M rows: bins are monotone in the value, ties share a bin, bin sizes follow the
     halving rule."""
