@@ -1,8 +1,8 @@
 """Node-range sharding of the ReFeX recursion across the GPUs of one box.
 
 Path A shards by output row: rank g owns the contiguous node range [lo_g, hi_g) (boundaries
-chosen so every rank traverses the same number of arcs -- power-law graphs put the hubs at the
-front), holds that slice of the CSR, a full replica of the current level's input matrix, and
+balance the ranks' level time: arcs gathered, and for the fused exchange also rows stored to the
+peers -- power-law graphs put the hubs at the front), holds that slice of the CSR, a full replica of the current level's input matrix, and
 produces its rows of the next level.  The one exchange step per level is an all-gather of the
 block the recursion continues on.  Primary form: the exchange is fused
 into the gather kernel -- every mean row is stored into all ranks' replicas of the next input
