@@ -6,7 +6,8 @@ not sm_100, calls raise.
 """
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libgraphrole_b200.so')
@@ -28,6 +29,7 @@ SIGNATURES = {
     'gr_csr_create': (c_int, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_void_p, c_void_p,
                               c_int, c_int]),
     'gr_csr_destroy': (c_int, [c_void_p]),
+    'gr_csr_tune_hot_rows': (c_int, [c_void_p, c_int64]),
     'gr_csr_info': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
                             POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     'gr_refex_aggregate_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
@@ -45,6 +47,10 @@ SIGNATURES = {
     'gr_peer_barrier_status': (c_int, [c_void_p, POINTER(c_int64)]),
     'gr_refex_levels_host_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                          c_void_p, c_void_p]),
+    'gr_refex_levels_host_sharded_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                                 c_int64, POINTER(c_void_p), POINTER(c_void_p),
+                                                 POINTER(c_void_p), c_int32, c_int32,
+                                                 POINTER(c_int64), c_void_p, c_void_p]),
     'gr_nmf_create': (c_int, [POINTER(c_void_p), c_int64, c_int32, c_int32, c_int]),
     'gr_nmf_destroy': (c_int, [c_void_p]),
     'gr_nmf_mu_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_double,
@@ -63,6 +69,31 @@ SIGNATURES = {
                                        c_void_p]),
     'gr_nmf_error_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  POINTER(c_double), c_void_p]),
+    'gr_quantizer_create': (c_int, [POINTER(c_void_p), c_int64, c_int]),
+    'gr_quantizer_destroy': (c_int, [c_void_p]),
+    'gr_quantizer_bind_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    'gr_quantizer_bind_f64': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    'gr_quantizer_encode_f32': (c_int, [c_void_p, c_int32, c_uint32, c_int32, c_double, c_void_p,
+                                        c_int64, POINTER(c_double), POINTER(c_int32),
+                                        POINTER(c_int64), c_void_p]),
+    'gr_quantizer_encode_f64': (c_int, [c_void_p, c_int32, c_uint32, c_int32, c_double, c_void_p,
+                                        c_int64, POINTER(c_double), POINTER(c_int32),
+                                        POINTER(c_int64), c_void_p]),
+    'gr_quantizer_count_distinct': (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
+    'gr_mdl_error_cost_f32': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_int32, POINTER(c_double), c_int,
+                                      c_void_p]),
+    'gr_mdl_error_cost_f64': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_int32, POINTER(c_double), c_int,
+                                      c_void_p]),
+    'gr_mdl_kl_f64': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
+                              POINTER(c_double), c_int, c_void_p]),
+    'gr_roles_f32': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_int64,
+                             c_int, c_void_p]),
+    'gr_roles_f64': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_int64,
+                             c_int, c_void_p]),
+    'gr_numpy_random_sample': (c_int, [c_uint32, c_int64, POINTER(c_double)]),
+    'gr_numpy_choice_uniform': (c_int, [c_uint32, c_int64, POINTER(c_int64)]),
 }
 
 
@@ -72,6 +103,13 @@ class NativeLibraryError(RuntimeError):
     def __init__(self, message, code=None):
         super().__init__(message)
         self.code = code
+
+
+class TooManyBinsError(ValueError):
+    """More quantisation bins than matrix entries: the ValueError scikit-learn's KMeans raises for
+    n_samples < n_clusters, which RoleExtractor's grid search expects and skips
+    (graphrole/roles/extract.py:127-129).  A class of its own so that the grid does not swallow
+    unrelated argument errors."""
 
 
 _lib = None
@@ -164,6 +202,10 @@ class CsrHandle:
         check(load().gr_csr_info(self._handle, *[byref(v) for v in vals]), 'gr_csr_info')
         keys = ('n_rows', 'n_cols', 'nnz', 'n_hub_rows', 'n_hub_segments', 'n_hot_rows')
         return {k: int(v.value) for k, v in zip(keys, vals)}
+
+    def tune_hot_rows(self, row_bytes):
+        """Re-tag the hot rows for feature rows of `row_bytes` bytes (cache hint only)."""
+        check(load().gr_csr_tune_hot_rows(self._handle, int(row_bytes)), 'gr_csr_tune_hot_rows')
 
     def aggregate(self, X, out=None, row_lo=0, row_hi=None, stream=None):
         """One recursion level.  X: [n_cols, d] fp32 (row stride free, unit column stride).
@@ -271,6 +313,30 @@ class CsrHandle:
                 {'sum': 0, 'mean': 1}[recurse_on], c_void_p(out_host.data_ptr()),
                 _stream_ptr(stream)), 'gr_refex_levels_host_f32')
         return out_host
+
+    def levels_host_sharded(self, X_host, col0, d, levels, row_offset, replicas_even,
+                            replicas_odd, flag_ptrs, rank, epoch, out_host, stream=None):
+        """gr_refex_levels_host_sharded_f32.  X_host: pinned float32 [n_cols, >= col0 + d];
+        out_host: [levels, n_rows, 2*d].  Returns the advanced barrier epoch."""
+        import torch
+        if X_host.dtype != torch.float32 or X_host.is_cuda or X_host.dim() != 2 \
+                or X_host.shape[0] != self.n_cols or X_host.stride(1) != 1 \
+                or X_host.shape[1] < col0 + d:
+            raise ValueError('X_host must be a float32 CPU [n_cols, >= col0 + d] tensor')
+        if tuple(out_host.shape) != (levels, self.n_rows, 2 * d) or not out_host.is_contiguous() \
+                or out_host.dtype != torch.float32:
+            raise ValueError('out_host must be contiguous float32 [levels, n_rows, 2*d]')
+        k = len(replicas_even)
+        ev = (c_void_p * k)(*[c_void_p(int(p)) for p in replicas_even])
+        od = (c_void_p * k)(*[c_void_p(int(p)) for p in replicas_odd])
+        fl = (c_void_p * k)(*[c_void_p(int(p)) for p in flag_ptrs])
+        ep = c_int64(int(epoch))
+        with torch.cuda.device(self.device):
+            check(load().gr_refex_levels_host_sharded_f32(
+                self._handle, c_void_p(X_host.data_ptr() + col0 * 4), X_host.stride(0), d, levels,
+                row_offset, ev, od, fl, k, rank, byref(ep), c_void_p(out_host.data_ptr()),
+                _stream_ptr(stream)), 'gr_refex_levels_host_sharded_f32')
+        return int(ep.value)
 
     def close(self):
         if getattr(self, '_handle', None):
@@ -455,3 +521,154 @@ def level0_features(rowptr, colidx, weights=None, directed=False, stream=None):
             c_void_p(out['external'].data_ptr()), dev.index or 0, _stream_ptr(stream)),
             'gr_level0_features_f64')
     return out
+
+
+class Quantizer:
+    """Owner of a gr_quantizer_t*: the Lloyd-Max quantiser of graphrole/roles/factor.py:29-49 on
+    the device.  bind() a float32 / float64 CUDA matrix once (sort + prefix sums), then encode()
+    it with as many bin counts as needed."""
+
+    KMEANS_SEED = 1          # factor.py:41 KMeans(random_state=1)
+    KMEANS_TOL = 1e-4        # sklearn defaults the reference relies on
+    KMEANS_MAX_ITER = 300
+
+    def __init__(self, capacity, device):
+        import torch
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise NativeLibraryError('the quantiser runs on CUDA devices only (no CPU fallback)')
+        self.device = device if device.index is not None else \
+            torch.device('cuda', torch.cuda.current_device())
+        self.capacity = int(capacity)
+        handle = c_void_p()
+        check(load().gr_quantizer_create(byref(handle), self.capacity, self.device.index),
+              'gr_quantizer_create')
+        self._handle = handle
+        self._bound = None
+
+    def bind(self, X, stream=None):
+        import torch
+        if not X.is_cuda or X.dim() != 2 or X.dtype not in (torch.float32, torch.float64):
+            raise ValueError('X must be a 2-D float32/float64 CUDA tensor')
+        if X.shape[1] > 1 and X.stride(1) != 1:
+            raise ValueError('X must have unit column stride')
+        fn = load().gr_quantizer_bind_f32 if X.dtype == torch.float32 else \
+            load().gr_quantizer_bind_f64
+        ld = X.stride(0) if X.shape[0] > 1 else X.shape[1]
+        with torch.cuda.device(self.device):
+            check(fn(self._handle, c_void_p(X.data_ptr()), X.shape[0], X.shape[1], ld,
+                     _stream_ptr(stream)), 'gr_quantizer_bind')
+        self._bound = X          # keep the matrix alive: the handle reads it again
+        return self
+
+    def encode(self, n_bins, out=None, seed=KMEANS_SEED, tol=KMEANS_TOL,
+               max_iter=KMEANS_MAX_ITER, stream=None):
+        """Returns (encoded matrix, info) with info = dict(centers, n_iter, n_distinct)."""
+        import numpy as np
+        import torch
+        X = self._bound
+        if X is None:
+            raise ValueError('bind() a matrix first')
+        if n_bins > X.numel():
+            raise TooManyBinsError(f'n_samples={X.numel()} should be >= n_clusters={n_bins}.')
+        if out is None:
+            out = torch.empty(X.shape, dtype=X.dtype, device=X.device)
+        if out.shape != X.shape or out.dtype != X.dtype or not out.is_contiguous():
+            raise ValueError('out must be a contiguous tensor of the bound matrix\'s shape/dtype')
+        fn = load().gr_quantizer_encode_f32 if X.dtype == torch.float32 else \
+            load().gr_quantizer_encode_f64
+        centers = (c_double * int(n_bins))()
+        n_iter, n_distinct = c_int32(0), c_int64(0)
+        with torch.cuda.device(self.device):
+            check(fn(self._handle, int(n_bins), int(seed), int(max_iter), float(tol),
+                     c_void_p(out.data_ptr()), X.shape[1], centers, byref(n_iter),
+                     byref(n_distinct), _stream_ptr(stream)), 'gr_quantizer_encode')
+        return out, {'centers': np.array(centers[:]), 'n_iter': int(n_iter.value),
+                     'n_distinct': int(n_distinct.value)}
+
+    def count_distinct(self, stream=None):
+        v = c_int64(0)
+        check(load().gr_quantizer_count_distinct(self._handle, byref(v), _stream_ptr(stream)),
+              'gr_quantizer_count_distinct')
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            load().gr_quantizer_destroy(self._handle)
+            self._handle = None
+            self._bound = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _matrix_args(t, name):
+    import torch
+    if not t.is_cuda or t.dim() != 2 or t.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f'{name} must be a 2-D float32/float64 CUDA tensor')
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f'{name} must have unit column stride')
+    return c_void_p(t.data_ptr()), (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def mdl_error_cost(V, G, F, stream=None):
+    """sum over V != 0 of v log(v / a) - v + a with a = G @ F (description_length.py:19, :44-61).
+    V [n, f], G [n, r], F [r, f]: CUDA tensors of one dtype (float32 or float64)."""
+    import torch
+    if not (V.dtype == G.dtype == F.dtype):
+        raise ValueError('V, G and F must share one dtype')
+    n, f = V.shape
+    r = G.shape[1]
+    if G.shape != (n, r) or F.shape != (r, f):
+        raise ValueError('shapes must be V [n, f], G [n, r], F [r, f]')
+    (pv, ldv), (pg, ldg), (pf, ldf) = (_matrix_args(t, k) for t, k in
+                                       ((V, 'V'), (G, 'G'), (F, 'F')))
+    fn = load().gr_mdl_error_cost_f32 if V.dtype == torch.float32 else \
+        load().gr_mdl_error_cost_f64
+    cost = c_double(0.0)
+    check(fn(pv, n, f, ldv, pg, ldg, pf, ldf, r, byref(cost), V.device.index or 0,
+             _stream_ptr(stream)), 'gr_mdl_error_cost')
+    return float(cost.value)
+
+
+def mdl_kl(V, V_approx, stream=None):
+    """The same cost from an explicit approximation (get_error_cost(V, V_approx)); float64."""
+    import torch
+    if V.dtype != torch.float64 or V_approx.dtype != torch.float64 or V.shape != V_approx.shape:
+        raise ValueError('V and V_approx must be float64 CUDA tensors of one shape')
+    (pv, ldv), (pa, lda) = _matrix_args(V, 'V'), _matrix_args(V_approx, 'V_approx')
+    cost = c_double(0.0)
+    check(load().gr_mdl_kl_f64(pv, pa, V.shape[0], V.shape[1], ldv, lda, byref(cost),
+                               V.device.index or 0, _stream_ptr(stream)), 'gr_mdl_kl_f64')
+    return float(cost.value)
+
+
+def roles(W, want_argmax=True, want_percentage=True, stream=None):
+    """(argmax int32 [n] or None, row-normalised W or None) of a node-role factor on the device."""
+    import torch
+    pw, ldw = _matrix_args(W, 'W')
+    n, r = W.shape
+    arg = torch.empty(n, dtype=torch.int32, device=W.device) if want_argmax else None
+    pct = torch.empty((n, r), dtype=W.dtype, device=W.device) if want_percentage else None
+    fn = load().gr_roles_f32 if W.dtype == torch.float32 else load().gr_roles_f64
+    check(fn(pw, n, r, ldw, c_void_p(arg.data_ptr() if arg is not None else 0),
+             c_void_p(pct.data_ptr() if pct is not None else 0), r, W.device.index or 0,
+             _stream_ptr(stream)), 'gr_roles')
+    return arg, pct
+
+
+def numpy_random_sample(seed, count):
+    """RandomState(seed).random_sample(count) as the library generates it (host only)."""
+    buf = (c_double * int(count))()
+    check(load().gr_numpy_random_sample(int(seed), int(count), buf), 'gr_numpy_random_sample')
+    return list(buf)
+
+
+def numpy_choice_uniform(seed, n):
+    """RandomState(seed).choice(n, p=np.full(n, 1 / n)) as the library computes it (host only)."""
+    v = c_int64(0)
+    check(load().gr_numpy_choice_uniform(int(seed), int(n), byref(v)), 'gr_numpy_choice_uniform')
+    return int(v.value)

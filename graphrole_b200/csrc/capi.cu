@@ -73,7 +73,9 @@ tag_hot_kernel(const int32_t* __restrict__ colidx, int64_t nnz, int64_t n_cols,
 // Tags arcs into the (at most) kHotBudgetBytes / kHotRowBytes rows of highest in-degree.
 int build_hot_tags(gr_csr* g) {
     if (g->nnz == 0 || g->n_cols == 0) return GR_OK;
-    const int64_t budget_rows = std::min<int64_t>(kHotBudgetBytes / kHotRowBytes, g->n_cols);
+    int64_t budget_bytes = kHotBudgetBytes;
+    if (const char* e = getenv("GR_CSR_HOT_BUDGET_MB")) budget_bytes = (int64_t)atoi(e) << 20;
+    const int64_t budget_rows = std::min<int64_t>(budget_bytes / g->hot_row_bytes, g->n_cols);
     int32_t* indeg = nullptr;
     unsigned long long* hist = nullptr;
     std::vector<unsigned long long> h_hist(kDegBins);
@@ -244,6 +246,22 @@ extern "C" int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int
 
     *out = g;
     return GR_OK;
+}
+
+extern "C" int gr_csr_tune_hot_rows(gr_csr_t* g, int64_t row_bytes) {
+    GR_REQUIRE(g != nullptr, "gr_csr_tune_hot_rows: handle is NULL");
+    GR_REQUIRE(row_bytes >= 4, "gr_csr_tune_hot_rows: row_bytes = %lld", (long long)row_bytes);
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", g->device);
+    // whole 32-byte sectors are what a gather occupies in L2
+    const int64_t bytes = (row_bytes + 31) / 32 * 32;
+    if (bytes == g->hot_row_bytes && g->d_colidx_tagged) return GR_OK;
+    GR_CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(g->d_colidx_tagged);
+    g->d_colidx_tagged = nullptr;
+    g->n_hot_rows = 0;
+    g->hot_row_bytes = bytes;
+    return build_hot_tags(g);
 }
 
 extern "C" int gr_csr_destroy(gr_csr_t* g) {

@@ -31,6 +31,7 @@ struct gr_csr {
     const int32_t* colidx = nullptr;  // caller-owned, device
     int32_t* d_colidx_tagged = nullptr;  // library-owned copy, sign bit = "hot row" (optional)
     int64_t n_hot_rows = 0;
+    int64_t hot_row_bytes = gr::kHotRowBytes;  // feature-row width the hot-row budget assumes
 
     // hub decomposition (library-owned)
     int64_t hub_threshold = gr::kHubThreshold, hub_segment = gr::kHubSegment;

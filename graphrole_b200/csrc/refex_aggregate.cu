@@ -104,31 +104,46 @@ __device__ __forceinline__ void load_row<1>(float (&v)[1], const float* p, bool 
     }
 }
 
+// The mean is the correctly rounded fp32 quotient sum / count (__fdiv_rn), never sum * (1 / count):
+// the reference divides in float64 (pandas mean), which keeps exact ties -- seven neighbours that
+// all carry 3.0 have mean exactly 3.0 -- and vertical_log_binning (prune.py:27-45) is rank based,
+// so a tie broken by a reciprocal's rounding error moves bin boundaries.  `count` is max(deg, 1)
+// (an empty row has sum 0).
 template <int VW>
-__device__ __forceinline__ void store_stream(float* p, const float (&v)[VW], float scale);
+__device__ __forceinline__ void store_sum(float* p, const float (&v)[VW]) {
+    if constexpr (VW == 4)
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    else
+        __stcs(p, v[0]);
+}
+
+template <int VW>
+__device__ __forceinline__ void store_stream(float* p, const float (&v)[VW], float count);
 
 template <>
-__device__ __forceinline__ void store_stream<4>(float* p, const float (&v)[4], float scale) {
+__device__ __forceinline__ void store_stream<4>(float* p, const float (&v)[4], float count) {
     __stcs(reinterpret_cast<float4*>(p),
-           make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale));
+           make_float4(__fdiv_rn(v[0], count), __fdiv_rn(v[1], count), __fdiv_rn(v[2], count),
+                       __fdiv_rn(v[3], count)));
 }
 template <>
-__device__ __forceinline__ void store_stream<1>(float* p, const float (&v)[1], float scale) {
-    __stcs(p, v[0] * scale);
+__device__ __forceinline__ void store_stream<1>(float* p, const float (&v)[1], float count) {
+    __stcs(p, __fdiv_rn(v[0], count));
 }
 
 // Replica stores (possibly to a peer GPU): default cache policy, write-back at L2 / posted over
 // NVLink.
 template <int VW>
-__device__ __forceinline__ void store_plain(float* p, const float (&v)[VW], float scale);
+__device__ __forceinline__ void store_plain(float* p, const float (&v)[VW], float count);
 template <>
-__device__ __forceinline__ void store_plain<4>(float* p, const float (&v)[4], float scale) {
+__device__ __forceinline__ void store_plain<4>(float* p, const float (&v)[4], float count) {
     *reinterpret_cast<float4*>(p) =
-        make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+        make_float4(__fdiv_rn(v[0], count), __fdiv_rn(v[1], count), __fdiv_rn(v[2], count),
+                    __fdiv_rn(v[3], count));
 }
 template <>
-__device__ __forceinline__ void store_plain<1>(float* p, const float (&v)[1], float scale) {
-    *p = v[0] * scale;
+__device__ __forceinline__ void store_plain<1>(float* p, const float (&v)[1], float count) {
+    *p = __fdiv_rn(v[0], count);
 }
 
 // ---- the warp's view of its contiguous colidx span --------------------------------------
@@ -228,7 +243,7 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
         float tot[VW];
         reduce_arcs<LPR, VW>(s, (uint32_t)(beg - base), s.limit, xcol, a.ldx, col_ok, lane,
                              pol_hot, tot);
-        if (col_ok && grp == 0) store_stream<VW>(a.partial + seg * a.d + col, tot, 1.f);
+        if (col_ok && grp == 0) store_sum<VW>(a.partial + seg * a.d + col, tot);
         return;
     }
 
@@ -256,15 +271,15 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
         if (!col_ok) continue;
         const int64_t o = (first + r) * a.ldo + col;
         // lane group 0 writes the sum block, group 1 (or the same lanes when LPR == 32) the mean
-        if (a.out_sum && grp == 0) store_stream<VW>(a.out_sum + o, tot, 1.f);
+        if (a.out_sum && grp == 0) store_sum<VW>(a.out_sum + o, tot);
         if constexpr (BCAST) {
             // lane group g writes replicas g, g + G, ...: remote stores are posted writes, the
             // groups only split the issue slots
-            const float inv = deg ? __frcp_rn((float)deg) : 0.f;
-            for (int p = grp; p < rep->n_rep; p += G) store_plain<VW>(rep->mean[p] + o, tot, inv);
+            const float cnt = (float)max(deg, 1u);
+            for (int p = grp; p < rep->n_rep; p += G) store_plain<VW>(rep->mean[p] + o, tot, cnt);
         } else {
             if (a.out_mean && grp == (G >= 2 ? 1 : 0))
-                store_stream<VW>(a.out_mean + o, tot, deg ? __frcp_rn((float)deg) : 0.f);
+                store_stream<VW>(a.out_mean + o, tot, (float)max(deg, 1u));
         }
     }
 }
@@ -293,13 +308,15 @@ hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict_
     if (h >= hub_hi) return;
     const int64_t row = hub_row[h];
     const int64_t s0 = hub_seg_first[h], s1 = hub_seg_first[h + 1];
-    const double deg = (double)(rowptr[row + 1] - rowptr[row]);
+    const float deg = (float)(rowptr[row + 1] - rowptr[row]);
     for (int c = lane; c < d; c += 32) {
         double acc = 0.0;
         for (int64_t s = s0; s < s1; ++s) acc += (double)partial[s * d + c];
-        if (out_sum) out_sum[row * ldo + c] = (float)acc;
-        if (out_mean) out_mean[row * ldo + c] = (float)(acc / deg);
-        for (int p = 0; p < rep.n_rep; ++p) rep.mean[p][row * ldo + c] = (float)(acc / deg);
+        // same rule as the ordinary rows: mean = fp32 sum / count, correctly rounded
+        const float sum = (float)acc, mean = __fdiv_rn(sum, deg);
+        if (out_sum) out_sum[row * ldo + c] = sum;
+        if (out_mean) out_mean[row * ldo + c] = mean;
+        for (int p = 0; p < rep.n_rep; ++p) rep.mean[p][row * ldo + c] = mean;
     }
 }
 
@@ -524,6 +541,93 @@ extern "C" int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_
         GR_CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)l * out_floats, out,
                                     out_floats * sizeof(float), cudaMemcpyDeviceToHost,
                                     g->copy_stream));
+        GR_CUDA_TRY(cudaEventRecord(g->ev_copied[slot], g->copy_stream));
+    }
+    GR_CUDA_TRY(cudaStreamSynchronize(g->copy_stream));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    return GR_OK;
+}
+
+// gr_peer_barrier lives in peer.cu
+extern "C" int gr_peer_barrier(void* const* flag_arrays, int32_t n_ranks, int32_t rank,
+                               int64_t epoch, double timeout_s, void* stream);
+
+// Host-buffer entry point of a node-range shard (one call per rank, all ranks of the exchange
+// group call it together): H2D of the whole level-0 input into the own replica, `levels` fused
+// gather + broadcast levels separated by flag barriers, and a D2H copy of the OWN rows of every
+// level on a second stream, overlapped with the next level.
+extern "C" int gr_refex_levels_host_sharded_f32(
+    gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d, int32_t levels, int64_t row_offset,
+    float* const* replicas_even, float* const* replicas_odd, void* const* flag_arrays,
+    int32_t n_ranks, int32_t rank, int64_t* epoch_inout, float* out_host, void* stream) {
+    GR_REQUIRE(g != nullptr, "gr_refex_levels_host_sharded_f32: handle is NULL");
+    GR_REQUIRE(X_host && out_host && replicas_even && replicas_odd && flag_arrays && epoch_inout,
+               "gr_refex_levels_host_sharded_f32: NULL argument");
+    GR_REQUIRE(d >= 1 && ldx >= d && levels >= 1, "gr_refex_levels_host_sharded_f32: bad d/ldx/levels");
+    GR_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxReplicas && rank >= 0 && rank < n_ranks,
+               "gr_refex_levels_host_sharded_f32: rank %d of %d", rank, n_ranks);
+    GR_REQUIRE(row_offset >= 0 && row_offset + g->n_rows <= g->n_cols,
+               "gr_refex_levels_host_sharded_f32: rows [%lld, %lld) outside [0, %lld)",
+               (long long)row_offset, (long long)(row_offset + g->n_rows), (long long)g->n_cols);
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", g->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // two local sum buffers (level l's D2H drains while level l + 1 runs)
+    const size_t sum_floats = (size_t)std::max<int64_t>(g->n_rows, 1) * (size_t)d;
+    if (g->stage_out_floats < sum_floats) {
+        for (int i = 0; i < 2; ++i) {
+            size_t have = g->stage_out_floats;
+            if (int rc = ensure_floats(&g->d_stage_out[i], &have, sum_floats)) return rc;
+        }
+        g->stage_out_floats = sum_floats;
+    }
+    if (!g->copy_stream) {
+        GR_CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GR_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_level[i], cudaEventDisableTiming));
+            GR_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+
+    float* const* reps[2] = {replicas_even, replicas_odd};
+    GR_CUDA_TRY(cudaMemcpy2DAsync(reps[0][rank], (size_t)d * sizeof(float), X_host,
+                                  (size_t)ldx * sizeof(float), (size_t)d * sizeof(float),
+                                  (size_t)g->n_cols, cudaMemcpyHostToDevice, st));
+    const size_t row_bytes = (size_t)d * sizeof(float);
+    const size_t out_pitch = 2 * row_bytes;
+    const size_t level_floats = (size_t)g->n_rows * 2 * (size_t)d;
+    for (int l = 0; l < levels; ++l) {
+        const int slot = l & 1;
+        const float* in = reps[slot][rank];
+        float* const* outs = reps[slot ^ 1];
+        float* sums = g->d_stage_out[slot];
+        // level l - 2 used this sum buffer, and its D2H read the own rows of the replica this
+        // level's kernel is about to overwrite
+        if (l >= 2) GR_CUDA_TRY(cudaStreamWaitEvent(st, g->ev_copied[slot], 0));
+        Replicas rep;
+        rep.n_rep = n_ranks;
+        for (int p = 0; p < kMaxReplicas; ++p)
+            rep.mean[p] = p < n_ranks ? outs[p] + (size_t)row_offset * d : nullptr;
+        if (int rc = aggregate_impl(g, in, d, d, 0, g->n_rows, sums, nullptr, d, &rep, st))
+            return rc;
+        GR_CUDA_TRY(cudaEventRecord(g->ev_level[slot], st));
+        if (n_ranks > 1) {
+            *epoch_inout += 1;
+            if (int rc = gr_peer_barrier(flag_arrays, n_ranks, rank, *epoch_inout, 0.0, st))
+                return rc;
+        }
+        if (g->n_rows > 0) {
+            GR_CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->ev_level[slot], 0));
+            float* dst = out_host + (size_t)l * level_floats;
+            GR_CUDA_TRY(cudaMemcpy2DAsync(dst, out_pitch, sums, row_bytes, row_bytes,
+                                          (size_t)g->n_rows, cudaMemcpyDeviceToHost,
+                                          g->copy_stream));
+            GR_CUDA_TRY(cudaMemcpy2DAsync(dst + d, out_pitch,
+                                          outs[rank] + (size_t)row_offset * d, row_bytes,
+                                          row_bytes, (size_t)g->n_rows, cudaMemcpyDeviceToHost,
+                                          g->copy_stream));
+        }
         GR_CUDA_TRY(cudaEventRecord(g->ev_copied[slot], g->copy_stream));
     }
     GR_CUDA_TRY(cudaStreamSynchronize(g->copy_stream));

@@ -1,0 +1,943 @@
+// RolX epilogue on the device ("next" #4): what RoleExtractor runs after the
+// NMF for every cell of its (n_roles, n_bits) grid --
+//
+//   encode             graphrole/roles/factor.py:29-49: Lloyd-Max quantiser = 1-D
+//                      KMeans(n_clusters=n_bins, random_state=1) over all entries of a factor
+//                      (sklearn/cluster/_kmeans.py: k-means++ :180-278, Lloyd :620-758)
+//   get_encoding_cost  graphrole/roles/description_length.py:32-41 (codebook size x entries)
+//   get_error_cost     graphrole/roles/description_length.py:44-61 (generalised KL of V and G.F)
+//   roles / role_percentage  graphrole/roles/extract.py:38-57 (row argmax / row normalisation)
+//
+// One-dimensional k-means has structure the generic algorithm does not use: after ONE sort of the
+// values and ONE prefix sum, a Lloyd iteration is k binary searches (cluster = contiguous range of
+// the sorted values) and k prefix-sum differences -- microseconds, independent of n -- so the whole
+// Lloyd loop, its convergence tests and the empty-cluster relocation run inside a single one-CTA
+// kernel launch, and the sort is shared by all the n_bins values the grid tries on one factor.
+// What stays O(n) per centre is sklearn's k-means++ seeding, which samples positions of the
+// ORIGINAL order proportionally to the squared distance to the nearest chosen centre: one scan,
+// one fused candidate evaluation and one update pass per centre, all HBM streaming kernels.
+// The random stream is NumPy's RandomState(seed) (mt19937.h), so labels equal scikit-learn's
+// whenever the data hold at least n_bins distinct values (otherwise scikit-learn's own result
+// depends on np.argpartition's order of equal keys; here every distinct value becomes a level).
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "mt19937.h"
+
+using namespace gr;
+
+namespace {
+
+constexpr int kMaxBins = 1024;
+constexpr int kMaxTrials = 8;          // 2 + int(ln(1024))
+constexpr int kRedBlocks = 148 * 4;    // fixed grid of the deterministic two-stage reductions
+constexpr int kRedThreads = 256;
+
+}  // namespace
+
+struct gr_quantizer {
+    int device = 0;
+    int64_t capacity = 0;
+    // bound matrix
+    const void* src = nullptr;
+    int is_f64 = 0;
+    int64_t rows = 0, cols = 0, ld = 0, N = 0;
+    double mean = 0.0, var = 0.0;
+    // device buffers (capacity entries each)
+    double* x = nullptr;        // centred values, original (row-major) order
+    double* xs = nullptr;       // the same values sorted ascending
+    double* P = nullptr;        // [N + 1] exclusive prefix sums of xs
+    double* closest = nullptr;  // k-means++: squared distance to the nearest chosen centre
+    double* cum = nullptr;      // k-means++: inclusive scan of `closest`
+    void* cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+    double* partial = nullptr;  // [kRedBlocks * kMaxTrials]
+    double* small = nullptr;    // device scratch: results of the reductions, candidates, ...
+    int64_t* small_i = nullptr;
+    double* lloyd_centers = nullptr;   // [kMaxBins]
+    double* thresholds = nullptr;      // [kMaxBins] first sorted value of every used cluster
+    double* levels = nullptr;          // [kMaxBins] centre (+ mean) of every used cluster
+    int32_t* lloyd_info = nullptr;     // [4] n_iter, n_used, strict, relocations
+    int64_t* lloyd_counts = nullptr;   // [kMaxBins]
+};
+
+namespace {
+
+// ---- deterministic reductions ---------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[kRedThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kRedThreads / 32; ++w) t += warp_part[w];
+    return t;   // valid in thread 0
+}
+
+template <typename T>
+__device__ __forceinline__ double load_value(const T* src, int64_t i, int64_t cols, int64_t ld) {
+    return (double)src[(i / cols) * ld + (i % cols)];
+}
+
+// stage 1 of sum(v): per-block partials
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+sum_kernel(const T* __restrict__ src, int64_t N, int64_t cols, int64_t ld,
+           double* __restrict__ partial) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads)
+        acc += load_value(src, i, cols, ld);
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// x = v - mean (sklearn centres the data, _kmeans.py:1486-1490) and sum x^2 for the variance
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+center_kernel(const T* __restrict__ src, int64_t N, int64_t cols, int64_t ld, double mean,
+              double* __restrict__ x, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads) {
+        const double c = load_value(src, i, cols, ld) - mean;
+        x[i] = c;
+        acc += c * c;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// stage 2: out[t] = sum over blocks of partial[b * stride + t], fixed order
+__global__ void finish_sum_kernel(const double* __restrict__ partial, int blocks, int stride,
+                                  int count, double* __restrict__ out) {
+    const int t = threadIdx.x;
+    if (t >= count) return;
+    double acc = 0.0;
+    for (int b = 0; b < blocks; ++b) acc += partial[b * stride + t];
+    out[t] = acc;
+}
+
+// ---- k-means++ ------------------------------------------------------------------------------
+// sklearn's squared distance for one feature (pairwise.py:377-412 through _kmeans.py:240, :257):
+// ((-2 (c x)) + c c) + x x, every operation rounded, clipped at 0.
+__device__ __forceinline__ double sk_sqdist(double c, double cc, double x) {
+    double d = -2.0 * __dmul_rn(c, x);
+    d = __dadd_rn(d, cc);
+    d = __dadd_rn(d, __dmul_rn(x, x));
+    return fmax(d, 0.0);
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+pp_init_kernel(const double* __restrict__ x, int64_t N, double c, double* __restrict__ closest,
+               double* __restrict__ partial) {
+    const double cc = __dmul_rn(c, c);
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads) {
+        const double d = sk_sqdist(c, cc, x[i]);
+        closest[i] = d;
+        acc += d;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// candidate_ids = clip(searchsorted(cumsum(closest), rand_vals), n - 1)  (_kmeans.py:250-254)
+__global__ void pp_search_kernel(const double* __restrict__ cum, const double* __restrict__ x,
+                                 int64_t N, const double* __restrict__ rand_vals, int trials,
+                                 int64_t* __restrict__ cand_idx, double* __restrict__ cand_x) {
+    const int t = threadIdx.x;
+    if (t >= trials) return;
+    const double v = rand_vals[t];
+    int64_t lo = 0, hi = N;                 // first index with cum[idx] >= v
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (cum[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    lo = min(lo, N - 1);
+    cand_idx[t] = lo;
+    cand_x[t] = x[lo];
+}
+
+// candidates_pot[t] = sum_i min(closest[i], dist(x[cand_t], x[i]))  (_kmeans.py:257-263)
+template <int TRIALS>
+__global__ void __launch_bounds__(kRedThreads)
+pp_eval_kernel(const double* __restrict__ x, const double* __restrict__ closest, int64_t N,
+               const double* __restrict__ cand_x, double* __restrict__ partial) {
+    double c[TRIALS], cc[TRIALS], acc[TRIALS];
+#pragma unroll
+    for (int t = 0; t < TRIALS; ++t) {
+        c[t] = cand_x[t];
+        cc[t] = __dmul_rn(c[t], c[t]);
+        acc[t] = 0.0;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads) {
+        const double xi = x[i], cl = closest[i];
+#pragma unroll
+        for (int t = 0; t < TRIALS; ++t) acc[t] += fmin(cl, sk_sqdist(c[t], cc[t], xi));
+    }
+#pragma unroll
+    for (int t = 0; t < TRIALS; ++t) {
+        const double s = block_sum(acc[t]);
+        if (threadIdx.x == 0) partial[blockIdx.x * kMaxTrials + t] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+pp_update_kernel(const double* __restrict__ x, int64_t N, double c, double* __restrict__ closest) {
+    const double cc = __dmul_rn(c, c);
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads)
+        closest[i] = fmin(closest[i], sk_sqdist(c, cc, x[i]));
+}
+
+// ---- the Lloyd loop: one CTA, everything in shared memory --------------------------------------
+// E-step score of sklearn's chunked Lloyd iteration (_k_means_lloyd.pyx: |c|^2 - 2 x.c through a
+// K = 1 GEMM): the smaller score wins, equal scores go to the smaller cluster index.
+__device__ __forceinline__ double sk_score(double c, double x) {
+    return __dadd_rn(__dmul_rn(c, c), -2.0 * __dmul_rn(x, c));
+}
+
+struct LloydShared {
+    double c[kMaxBins];        // centres by cluster index
+    double c_old[kMaxBins];
+    double cs[kMaxBins];       // centres in sorted order
+    double sum[kMaxBins];      // by sorted position (relocation edits it)
+    int64_t start[kMaxBins + 1];      // E step: first sorted value of the range at a position
+    int64_t start_prev[kMaxBins + 1]; // previous E step, for the "labels unchanged" test
+    int64_t cnt_e[kMaxBins];   // E-step sizes by sorted position
+    int64_t cnt[kMaxBins];     // sizes after relocation
+    int ord[kMaxBins];         // sorted position -> cluster index
+    int ord_prev[kMaxBins];
+    int pos[kMaxBins];         // cluster index -> sorted position
+    int strip_lo[kMaxBins], strip_hi[kMaxBins];   // points relocation took from a range's ends
+    unsigned char active[kMaxBins];
+    double red[32];
+    int ired[32];
+};
+
+// sorted order of the centres by (value, cluster index): rank by counting, k <= 1024
+__device__ void lloyd_sort_centres(LloydShared& s, int k) {
+    const int j = threadIdx.x;
+    if (j < k) {
+        const double cj = s.c[j];
+        int rank = 0;
+        for (int i = 0; i < k; ++i) {
+            const double ci = s.c[i];
+            rank += (ci < cj || (ci == cj && i < j)) ? 1 : 0;
+        }
+        s.cs[rank] = cj;
+        s.ord[rank] = j;
+        s.pos[j] = rank;
+    }
+    __syncthreads();
+    // equal centres: only the first (smallest cluster index) can win a point
+    if (j < k) s.active[j] = (j == 0 || s.cs[j] != s.cs[j - 1]) ? 1 : 0;
+    __syncthreads();
+}
+
+// E step on the sorted values: range of sorted position p = [start[p], start[p + 1]).
+__device__ void lloyd_assign(LloydShared& s, int k, const double* __restrict__ xs, int64_t N) {
+    const int p = threadIdx.x;
+    if (p < k) {
+        int64_t b = 0;
+        if (s.active[p]) {
+            int q = p - 1;                        // previous active centre
+            while (q >= 0 && !s.active[q]) --q;
+            if (q >= 0) {
+                const double lo_c = s.cs[q], hi_c = s.cs[p];
+                const int lo_i = s.ord[q], hi_i = s.ord[p];
+                int64_t lo = 0, hi = N;           // first value that prefers the upper centre
+                while (lo < hi) {
+                    const int64_t mid = lo + (hi - lo) / 2;
+                    const double xv = xs[mid];
+                    const double su = sk_score(hi_c, xv), sl = sk_score(lo_c, xv);
+                    const bool upper = su < sl || (su == sl && hi_i < lo_i);
+                    if (upper) hi = mid; else lo = mid + 1;
+                }
+                b = lo;
+            }
+        }
+        s.start[p] = b;
+    }
+    if (p == 0) s.start[k] = N;
+    __syncthreads();
+    if (p == 0) {
+        // boundaries non-decreasing; a position whose centre duplicates an earlier one is empty
+        int64_t run = 0;
+        for (int q = 0; q < k; ++q) {
+            if (s.active[q]) run = max(run, s.start[q]);
+            s.start[q] = run;
+        }
+        for (int q = k - 1; q >= 0; --q)
+            if (!s.active[q]) s.start[q] = s.start[q + 1];
+    }
+    __syncthreads();
+    if (p < k) s.cnt_e[p] = s.start[p + 1] - s.start[p];
+    __syncthreads();
+}
+
+// info: [0] n_iter  [1] number of used clusters  [2] strict convergence  [3] relocations
+__global__ void __launch_bounds__(kMaxBins)
+lloyd_kernel(const double* __restrict__ xs, const double* __restrict__ P, int64_t N, int k,
+             double* __restrict__ centres, double tol, int max_iter, double mean,
+             int32_t* __restrict__ info, int64_t* __restrict__ counts_out,
+             double* __restrict__ thresholds, double* __restrict__ levels) {
+    extern __shared__ __align__(16) unsigned char lloyd_smem[];
+    LloydShared& s = *reinterpret_cast<LloydShared*>(lloyd_smem);
+    const int p = threadIdx.x;
+    const int n_warps = (int)(blockDim.x >> 5);
+    if (p < k) {
+        s.c[p] = centres[p];
+        s.ord_prev[p] = -1;
+    }
+    if (p <= k) s.start_prev[p] = -1;
+    __syncthreads();
+
+    bool strict = false;
+    int n_iter = 0, relocations = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        n_iter = it + 1;
+        lloyd_sort_centres(s, k);
+        lloyd_assign(s, k, xs, N);
+        if (p < k) {
+            s.sum[p] = P[s.start[p + 1]] - P[s.start[p]];
+            s.cnt[p] = s.cnt_e[p];
+            s.strip_lo[p] = s.strip_hi[p] = 0;
+            s.c_old[p] = s.c[p];
+        }
+        __syncthreads();
+
+        // empty clusters take the points farthest from their E-step centres
+        // (_k_means_common.pyx, _relocate_empty_clusters_dense); serial and rare
+        if (p == 0) {
+            for (int j = 0; j < k; ++j) {          // np.where(weight == 0)[0] order
+                const int pj = s.pos[j];
+                if (s.cnt_e[pj] != 0) continue;
+                double best = -1.0;
+                int bq = -1;
+                bool at_lo = true;
+                for (int q = 0; q < k; ++q) {
+                    const int64_t left = s.cnt_e[q] - s.strip_lo[q] - s.strip_hi[q];
+                    if (left <= 0) continue;
+                    const double cq = s.c_old[s.ord[q]];
+                    const double xl = xs[s.start[q] + s.strip_lo[q]];
+                    const double xh = xs[s.start[q + 1] - 1 - s.strip_hi[q]];
+                    const double dl = (xl - cq) * (xl - cq), dh = (xh - cq) * (xh - cq);
+                    if (dl > best) { best = dl; bq = q; at_lo = true; }
+                    if (dh > best) { best = dh; bq = q; at_lo = false; }
+                }
+                if (bq < 0) break;
+                const double xv = at_lo ? xs[s.start[bq] + s.strip_lo[bq]]
+                                        : xs[s.start[bq + 1] - 1 - s.strip_hi[bq]];
+                if (at_lo) s.strip_lo[bq] += 1; else s.strip_hi[bq] += 1;
+                s.sum[bq] -= xv;
+                s.cnt[bq] -= 1;
+                s.sum[pj] = xv;
+                s.cnt[pj] = 1;
+                ++relocations;
+            }
+        }
+        __syncthreads();
+
+        // M step (_average_centers: centre = sum * (1 / weight); a cluster left without weight
+        // keeps its raw sum) and the centre shift
+        double sh2 = 0.0;
+        int same = 1;
+        if (p < k) {
+            const int j = s.ord[p];
+            if (s.cnt[p] > 0) s.c[j] = s.sum[p] * (1.0 / (double)s.cnt[p]);
+            else if (s.cnt_e[p] > 0) s.c[j] = s.sum[p];
+            const double dlt = s.c[j] - s.c_old[j];
+            sh2 = dlt * dlt;
+            // labels unchanged <=> every non-empty range existed, with the same cluster index, in
+            // the previous E step (both sets of ranges tile [0, N))
+            if (s.cnt_e[p] > 0) {
+                same = 0;
+                for (int q = 0; q < k; ++q)
+                    if (s.start_prev[q] == s.start[p] && s.start_prev[q + 1] == s.start[p + 1] &&
+                        s.ord_prev[q] == j) { same = 1; break; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sh2 += __shfl_xor_sync(0xffffffffu, sh2, o);
+        const unsigned warp_same = __all_sync(0xffffffffu, same != 0);
+        if ((p & 31) == 0) {
+            s.red[p >> 5] = sh2;
+            s.ired[p >> 5] = warp_same ? 1 : 0;
+        }
+        __syncthreads();
+        double shift_tot = 0.0;
+        int all_same = 1;
+        for (int w = 0; w < n_warps; ++w) {
+            shift_tot += s.red[w];
+            all_same &= s.ired[w];
+        }
+        __syncthreads();
+        if (all_same) { strict = true; break; }        // _kmeans.py:723-728
+        if (shift_tot <= tol) break;                   // :731-738
+        if (p < k) s.ord_prev[p] = s.ord[p];
+        if (p <= k) s.start_prev[p] = s.start[p];
+        __syncthreads();
+    }
+    // labels that go with the final centres: the last E step under strict convergence, otherwise
+    // one more E step (_kmeans.py:742-754)
+    if (!strict) {
+        lloyd_sort_centres(s, k);
+        lloyd_assign(s, k, xs, N);
+    }
+    if (p < k) counts_out[s.ord[p]] = s.cnt_e[p];
+    if (p == 0) {
+        int m = 0;
+        for (int q = 0; q < k; ++q) {
+            if (s.cnt_e[q] <= 0) continue;
+            thresholds[m] = xs[s.start[q]];
+            levels[m] = s.c[s.ord[q]] + mean;          // best_centers += X_mean, :1546
+            ++m;
+        }
+        info[0] = n_iter;
+        info[1] = m;
+        info[2] = strict ? 1 : 0;
+        info[3] = relocations;
+    }
+    if (p < k) centres[p] = s.c[p] + mean;
+}
+
+// out[i] = level of the range that holds x[i] (graphrole/roles/factor.py:48)
+template <typename T>
+__global__ void __launch_bounds__(256)
+quantize_kernel(const double* __restrict__ x, int64_t N, int64_t cols, int64_t ldo,
+                const double* __restrict__ thresholds, const double* __restrict__ levels,
+                int n_used, T* __restrict__ out) {
+    __shared__ double th[kMaxBins], lv[kMaxBins];
+    for (int i = threadIdx.x; i < n_used; i += blockDim.x) {
+        th[i] = thresholds[i];
+        lv[i] = levels[i];
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double xv = x[i];
+        int lo = 0, hi = n_used;                    // last m with th[m] <= xv
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (th[mid] <= xv) lo = mid; else hi = mid;
+        }
+        out[(i / cols) * ldo + (i % cols)] = (T)lv[lo];
+    }
+}
+
+// fewer distinct values than bins: every distinct value is its own level (out = in)
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_matrix_kernel(const T* __restrict__ src, int64_t N, int64_t cols, int64_t ld, int64_t ldo,
+                   T* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[(i / cols) * ldo + (i % cols)] = src[(i / cols) * ld + (i % cols)];
+}
+
+// number of distinct values of a sorted array
+__global__ void __launch_bounds__(kRedThreads)
+count_runs_kernel(const double* __restrict__ xs, int64_t N, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * kRedThreads)
+        acc += (i == 0 || xs[i] != xs[i - 1]) ? 1.0 : 0.0;
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// ---- description length --------------------------------------------------------------------
+// error cost: sum over v != 0 of v log(v / v') - v + v' with v' = (G F)[i, j]
+// (description_length.py:44-61), fp64 arithmetic whatever the storage type.  One CTA per row
+// block; F (r x f) is read through L1/L2 (r f <= 32 x 1024 values).
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+kl_cost_kernel(const T* __restrict__ V, int64_t n, int f, int64_t ldv, const T* __restrict__ G,
+               int64_t ldg, const T* __restrict__ F, int64_t ldf, int r,
+               double* __restrict__ partial) {
+    __shared__ double g_row[64];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < r) g_row[threadIdx.x] = (double)G[i * ldg + threadIdx.x];
+        __syncthreads();
+        for (int j = threadIdx.x; j < f; j += kRedThreads) {
+            const double v = (double)V[i * ldv + j];
+            if (v != 0.0) {
+                double a = 0.0;
+                for (int q = 0; q < r; ++q) a = fma(g_row[q], (double)__ldg(F + q * ldf + j), a);
+                acc += (v * log(v / a) - v) + a;
+            }
+        }
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// same cost from an explicit approximation matrix (get_error_cost(V, V_approx))
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+kl_pair_kernel(const T* __restrict__ V, const T* __restrict__ A, int64_t n, int f, int64_t ldv,
+               int64_t lda, double* __restrict__ partial) {
+    double acc = 0.0;
+    const int64_t total = n * f;
+    for (int64_t e = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * kRedThreads) {
+        const int64_t i = e / f, j = e % f;
+        const double v = (double)V[i * ldv + j];
+        if (v != 0.0) {
+            const double a = (double)A[i * lda + j];
+            acc += (v * log(v / a) - v) + a;
+        }
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// roles / role_percentage (roles/extract.py:38-57): first maximum of every row, row / row sum
+template <typename T>
+__global__ void __launch_bounds__(256)
+roles_kernel(const T* __restrict__ W, int64_t n, int r, int64_t ldw, int32_t* __restrict__ argmax,
+             T* __restrict__ pct, int64_t ldp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const T* row = W + i * ldw;
+        T best = row[0], tot = row[0];
+        int arg = 0;
+        for (int q = 1; q < r; ++q) {
+            const T v = row[q];
+            tot += v;
+            if (v > best) { best = v; arg = q; }
+        }
+        if (argmax) argmax[i] = arg;
+        if (pct)
+            for (int q = 0; q < r; ++q) pct[i * ldp + q] = row[q] / tot;
+    }
+}
+
+int reduce_blocks(int64_t N) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(kRedBlocks, ceil_div<int64_t>(N, kRedThreads)));
+}
+
+// sum of `count` per-block partial vectors -> host
+int finish_to_host(gr_quantizer* q, int blocks, int stride, int count, double* host,
+                   cudaStream_t st) {
+    finish_sum_kernel<<<1, 32, 0, st>>>(q->partial, blocks, stride, count, q->small);
+    count_launch();
+    GR_CUDA_TRY(cudaGetLastError());
+    GR_CUDA_TRY(cudaMemcpyAsync(host, q->small, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    return GR_OK;
+}
+
+template <typename T>
+int bind_impl(gr_quantizer* q, const T* X, int64_t rows, int64_t cols, int64_t ld, void* stream) {
+    GR_REQUIRE(q != nullptr, "gr_quantizer_bind: handle is NULL");
+    GR_REQUIRE(X != nullptr && rows >= 1 && cols >= 1 && ld >= cols,
+               "gr_quantizer_bind: bad matrix (rows %lld, cols %lld, ld %lld)", (long long)rows,
+               (long long)cols, (long long)ld);
+    const int64_t N = rows * cols;
+    GR_REQUIRE(N <= q->capacity, "gr_quantizer_bind: %lld entries exceed the capacity %lld",
+               (long long)N, (long long)q->capacity);
+    DeviceGuard guard(q->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", q->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = reduce_blocks(N);
+
+    double h = 0.0;
+    sum_kernel<T><<<blocks, kRedThreads, 0, st>>>(X, N, cols, ld, q->partial);
+    count_launch();
+    if (int rc = finish_to_host(q, blocks, 1, 1, &h, st)) return rc;
+    q->mean = h / (double)N;
+    center_kernel<T><<<blocks, kRedThreads, 0, st>>>(X, N, cols, ld, q->mean, q->x, q->partial);
+    count_launch();
+    if (int rc = finish_to_host(q, blocks, 1, 1, &h, st)) return rc;
+    q->var = h / (double)N;
+
+    size_t need = q->cub_temp_bytes;
+    GR_CUDA_TRY(cub::DeviceRadixSort::SortKeys(q->cub_temp, need, q->x, q->xs, N, 0, 64, st));
+    GR_CUDA_TRY(cudaMemsetAsync(q->P, 0, sizeof(double), st));
+    need = q->cub_temp_bytes;
+    GR_CUDA_TRY(cub::DeviceScan::InclusiveSum(q->cub_temp, need, q->xs, q->P + 1, N, st));
+    count_launch(6);   // cub: radix-sort passes + scan
+    q->src = X;
+    q->is_f64 = sizeof(T) == 8;
+    q->rows = rows;
+    q->cols = cols;
+    q->ld = ld;
+    q->N = N;
+    return GR_OK;
+}
+
+// RandomState.choice(n, p = 1/n): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right').
+// The sequential cumsum of a constant is emulated only when floor(u n) is not provably the answer
+// (and n is small enough to afford it); beyond 2^24 entries floor(u n) is used as is.
+int64_t choice_uniform(int64_t n, double u) {
+    int64_t i0 = std::min<int64_t>((int64_t)(u * (double)n), n - 1);
+    const double slack = ((double)n + 8.0) * 2.220446049250313e-16;
+    const bool safe_hi = (double)(i0 + 1) / (double)n * (1.0 - slack) > u;
+    const bool safe_lo = i0 == 0 || (double)i0 / (double)n * (1.0 + slack) <= u;
+    if ((safe_hi && safe_lo) || n > (1ll << 24)) return i0;
+    const double c = 1.0 / (double)n;
+    volatile double tot = 0.0;
+    for (int64_t i = 0; i < n; ++i) tot = tot + c;
+    const double last = tot;
+    volatile double run = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        run = run + c;
+        if (run / last > u) return i;
+    }
+    return n - 1;
+}
+
+template <int TRIALS>
+void launch_eval(gr_quantizer* q, int blocks, cudaStream_t st, const double* cand_x) {
+    pp_eval_kernel<TRIALS><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, q->N, cand_x,
+                                                           q->partial);
+}
+
+template <typename T>
+int encode_impl(gr_quantizer* q, int32_t n_bins, uint32_t seed, int32_t max_iter, double tol,
+                T* out, int64_t ldo, double* centers_out, int32_t* n_iter_out,
+                int64_t* n_distinct_out, void* stream) {
+    GR_REQUIRE(q != nullptr && q->src != nullptr, "gr_quantizer_encode: no matrix is bound");
+    GR_REQUIRE(q->is_f64 == (sizeof(T) == 8), "gr_quantizer_encode: dtype differs from bind");
+    GR_REQUIRE(out != nullptr && ldo >= q->cols, "gr_quantizer_encode: bad output");
+    GR_REQUIRE(n_bins >= 1 && n_bins <= kMaxBins, "gr_quantizer_encode: n_bins = %d outside [1, %d]",
+               n_bins, kMaxBins);
+    // the message sklearn raises (KMeans._check_params_vs_input); callers of the reference rely
+    // on this ValueError to skip grid cells (roles/extract.py:127-129)
+    GR_REQUIRE(q->N >= n_bins, "n_samples=%lld should be >= n_clusters=%d.", (long long)q->N, n_bins);
+    DeviceGuard guard(q->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", q->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = q->N;
+    const int blocks = reduce_blocks(N);
+    const int k = n_bins;
+    const int trials = 2 + (int)std::log((double)k);
+
+    // ---- k-means++ seeding (_kmeans.py:180-278) ------------------------------------------------
+    NumpyRandomState rs(seed);
+    std::vector<double> centres((size_t)k);
+    double h[kMaxTrials];
+    double* d_rand = q->small + 16;
+    double* d_cand_x = q->small + 32;
+    int64_t* d_cand_i = q->small_i;
+    const int64_t first = choice_uniform(N, rs.random_sample());
+    GR_CUDA_TRY(cudaMemcpyAsync(&centres[0], q->x + first, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    pp_init_kernel<<<blocks, kRedThreads, 0, st>>>(q->x, N, centres[0], q->closest, q->partial);
+    count_launch();
+    double pot = 0.0;
+    if (int rc = finish_to_host(q, blocks, 1, 1, &pot, st)) return rc;
+    bool degenerate = false;
+    for (int c = 1; c < k; ++c) {
+        if (!(pot > 0.0)) { degenerate = true; break; }   // every distinct value is a centre already
+        for (int t = 0; t < trials; ++t) h[t] = rs.random_sample() * pot;
+        GR_CUDA_TRY(cudaMemcpyAsync(d_rand, h, trials * sizeof(double), cudaMemcpyHostToDevice, st));
+        size_t need = q->cub_temp_bytes;
+        GR_CUDA_TRY(cub::DeviceScan::InclusiveSum(q->cub_temp, need, q->closest, q->cum, N, st));
+        pp_search_kernel<<<1, 32, 0, st>>>(q->cum, q->x, N, d_rand, trials, d_cand_i, d_cand_x);
+        switch (trials) {
+            case 2: launch_eval<2>(q, blocks, st, d_cand_x); break;
+            case 3: launch_eval<3>(q, blocks, st, d_cand_x); break;
+            case 4: launch_eval<4>(q, blocks, st, d_cand_x); break;
+            case 5: launch_eval<5>(q, blocks, st, d_cand_x); break;
+            case 6: launch_eval<6>(q, blocks, st, d_cand_x); break;
+            case 7: launch_eval<7>(q, blocks, st, d_cand_x); break;
+            default: launch_eval<8>(q, blocks, st, d_cand_x); break;
+        }
+        count_launch(4);
+        GR_CUDA_TRY(cudaGetLastError());
+        double pots[kMaxTrials], cx[kMaxTrials];
+        finish_sum_kernel<<<1, 32, 0, st>>>(q->partial, blocks, kMaxTrials, trials, q->small);
+        count_launch();
+        GR_CUDA_TRY(cudaMemcpyAsync(pots, q->small, trials * sizeof(double), cudaMemcpyDeviceToHost, st));
+        GR_CUDA_TRY(cudaMemcpyAsync(cx, d_cand_x, trials * sizeof(double), cudaMemcpyDeviceToHost, st));
+        GR_CUDA_TRY(cudaStreamSynchronize(st));
+        int best = 0;                                       // np.argmin: first minimum
+        for (int t = 1; t < trials; ++t) if (pots[t] < pots[best]) best = t;
+        pot = pots[best];
+        centres[(size_t)c] = cx[best];
+        pp_update_kernel<<<blocks, kRedThreads, 0, st>>>(q->x, N, cx[best], q->closest);
+        count_launch();
+    }
+
+    if (degenerate) {
+        // fewer distinct values than bins: exact quantisation, every distinct value a level
+        copy_matrix_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(q->src), N, q->cols,
+                                                      q->ld, ldo, out);
+        count_runs_kernel<<<blocks, kRedThreads, 0, st>>>(q->xs, N, q->partial);
+        count_launch(2);
+        double runs = 0.0;
+        if (int rc = finish_to_host(q, blocks, 1, 1, &runs, st)) return rc;
+        if (n_distinct_out) *n_distinct_out = (int64_t)runs;
+        if (n_iter_out) *n_iter_out = 0;
+        if (centers_out)
+            for (int c = 0; c < k; ++c) centers_out[c] = std::nan("");
+        return GR_OK;
+    }
+
+    // ---- Lloyd loop, one launch (_kmeans.py:620-758) -------------------------------------------
+    GR_CUDA_TRY(cudaMemcpyAsync(q->lloyd_centers, centres.data(), k * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+    GR_CUDA_TRY(cudaFuncSetAttribute(lloyd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(LloydShared)));
+    const int threads = std::max(32, (k + 31) / 32 * 32);
+    lloyd_kernel<<<1, threads, sizeof(LloydShared), st>>>(
+        q->xs, q->P, N, k, q->lloyd_centers, q->var * tol, max_iter, q->mean, q->lloyd_info,
+        q->lloyd_counts, q->thresholds, q->levels);
+    count_launch();
+    GR_CUDA_TRY(cudaGetLastError());
+    int32_t info[4];
+    GR_CUDA_TRY(cudaMemcpyAsync(info, q->lloyd_info, sizeof(info), cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaMemcpyAsync(centres.data(), q->lloyd_centers, k * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    const int n_used = info[1];
+    quantize_kernel<T><<<blocks, 256, 0, st>>>(q->x, N, q->cols, ldo, q->thresholds, q->levels,
+                                               n_used, out);
+    count_launch();
+    GR_CUDA_TRY(cudaGetLastError());
+    if (n_distinct_out) {
+        std::vector<double> lv((size_t)n_used);
+        GR_CUDA_TRY(cudaMemcpyAsync(lv.data(), q->levels, n_used * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        GR_CUDA_TRY(cudaStreamSynchronize(st));
+        if (sizeof(T) == 4)
+            for (auto& v : lv) v = (double)(float)v;      // what the output actually holds
+        std::sort(lv.begin(), lv.end());
+        *n_distinct_out = (int64_t)(std::unique(lv.begin(), lv.end()) - lv.begin());
+    }
+    if (n_iter_out) *n_iter_out = info[0];
+    if (centers_out)
+        for (int c = 0; c < k; ++c) centers_out[c] = centres[(size_t)c];
+    return GR_OK;
+}
+
+template <typename T>
+int kl_impl(const T* V, int64_t n, int32_t f, int64_t ldv, const T* G, int64_t ldg, const T* F,
+            int64_t ldf, int32_t r, double* cost_out, int device, void* stream) {
+    GR_REQUIRE(V && G && F && cost_out, "gr_mdl_error_cost: NULL argument");
+    GR_REQUIRE(n >= 1 && f >= 1 && r >= 1 && r <= 64, "gr_mdl_error_cost: n/f/r = %lld/%d/%d (r <= 64)",
+               (long long)n, f, r);
+    GR_REQUIRE(ldv >= f && ldg >= r && ldf >= f, "gr_mdl_error_cost: row strides too small");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (int)std::min<int64_t>(n, kRedBlocks * 2);
+    double* partial = nullptr;
+    GR_CUDA_TRY(cudaMallocAsync(&partial, (blocks + 1) * sizeof(double), st));
+    kl_cost_kernel<T><<<blocks, kRedThreads, 0, st>>>(V, n, f, ldv, G, ldg, F, ldf, r, partial);
+    finish_sum_kernel<<<1, 32, 0, st>>>(partial, blocks, 1, 1, partial + blocks);
+    count_launch(2);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cost_out, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(partial, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(GR_ERR_CUDA, "gr_mdl_error_cost: %s", cudaGetErrorString(e));
+    return GR_OK;
+}
+
+template <typename T>
+int kl_pair_impl(const T* V, const T* A, int64_t n, int32_t f, int64_t ldv, int64_t lda,
+                 double* cost_out, int device, void* stream) {
+    GR_REQUIRE(V && A && cost_out, "gr_mdl_kl: NULL argument");
+    GR_REQUIRE(n >= 1 && f >= 1 && ldv >= f && lda >= f, "gr_mdl_kl: bad shape");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = reduce_blocks(n * f);
+    double* partial = nullptr;
+    GR_CUDA_TRY(cudaMallocAsync(&partial, (blocks + 1) * sizeof(double), st));
+    kl_pair_kernel<T><<<blocks, kRedThreads, 0, st>>>(V, A, n, f, ldv, lda, partial);
+    finish_sum_kernel<<<1, 32, 0, st>>>(partial, blocks, 1, 1, partial + blocks);
+    count_launch(2);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cost_out, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(partial, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(GR_ERR_CUDA, "gr_mdl_kl: %s", cudaGetErrorString(e));
+    return GR_OK;
+}
+
+template <typename T>
+int roles_impl(const T* W, int64_t n, int32_t r, int64_t ldw, int32_t* argmax, T* pct, int64_t ldp,
+               int device, void* stream) {
+    GR_REQUIRE(W != nullptr && n >= 1 && r >= 1 && ldw >= r, "gr_roles: bad factor matrix");
+    GR_REQUIRE(argmax != nullptr || pct != nullptr, "gr_roles: both outputs are NULL");
+    GR_REQUIRE(pct == nullptr || ldp >= r, "gr_roles: ldp < r");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", device);
+    const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256), 148 * 8);
+    roles_kernel<T><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, n, r, ldw, argmax, pct,
+                                                                          ldp);
+    count_launch();
+    GR_CUDA_TRY(cudaGetLastError());
+    return GR_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" int gr_quantizer_create(gr_quantizer_t** out, int64_t capacity, int device) {
+    GR_REQUIRE(out != nullptr, "gr_quantizer_create: out is NULL");
+    *out = nullptr;
+    GR_REQUIRE(capacity >= 1, "gr_quantizer_create: capacity = %lld", (long long)capacity);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "gr_quantizer_create: cannot select device %d", device);
+    if (int rc = require_sm100(device)) return rc;
+    gr_quantizer* q = new (std::nothrow) gr_quantizer();
+    if (!q) return fail(GR_ERR_OUT_OF_MEMORY, "gr_quantizer_create: host allocation failed");
+    q->device = device;
+    q->capacity = capacity;
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr,
+                                   capacity, 0, 64);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const double*)nullptr, (double*)nullptr,
+                                  capacity);
+    q->cub_temp_bytes = std::max(sort_bytes, scan_bytes) + 256;
+    const size_t nb = (size_t)capacity * sizeof(double);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc((void**)&q->x, nb);
+    alloc((void**)&q->xs, nb);
+    alloc((void**)&q->P, nb + sizeof(double));
+    alloc((void**)&q->closest, nb);
+    alloc((void**)&q->cum, nb);
+    alloc(&q->cub_temp, q->cub_temp_bytes);
+    alloc((void**)&q->partial, (size_t)kRedBlocks * kMaxTrials * sizeof(double));
+    alloc((void**)&q->small, 64 * sizeof(double));
+    alloc((void**)&q->small_i, 16 * sizeof(int64_t));
+    alloc((void**)&q->lloyd_centers, kMaxBins * sizeof(double));
+    alloc((void**)&q->thresholds, kMaxBins * sizeof(double));
+    alloc((void**)&q->levels, kMaxBins * sizeof(double));
+    alloc((void**)&q->lloyd_info, 4 * sizeof(int32_t));
+    alloc((void**)&q->lloyd_counts, kMaxBins * sizeof(int64_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        gr_quantizer_destroy(q);
+        return fail(e == cudaErrorMemoryAllocation ? GR_ERR_OUT_OF_MEMORY : GR_ERR_CUDA,
+                    "gr_quantizer_create: %s", cudaGetErrorString(e));
+    }
+    *out = q;
+    return GR_OK;
+}
+
+extern "C" int gr_quantizer_destroy(gr_quantizer_t* q) {
+    if (!q) return GR_OK;
+    DeviceGuard guard(q->device);
+    cudaFree(q->x);
+    cudaFree(q->xs);
+    cudaFree(q->P);
+    cudaFree(q->closest);
+    cudaFree(q->cum);
+    cudaFree(q->cub_temp);
+    cudaFree(q->partial);
+    cudaFree(q->small);
+    cudaFree(q->small_i);
+    cudaFree(q->lloyd_centers);
+    cudaFree(q->thresholds);
+    cudaFree(q->levels);
+    cudaFree(q->lloyd_info);
+    cudaFree(q->lloyd_counts);
+    delete q;
+    return GR_OK;
+}
+
+extern "C" int gr_quantizer_bind_f32(gr_quantizer_t* q, const float* X_dev, int64_t rows,
+                                     int64_t cols, int64_t ld, void* stream) {
+    return bind_impl<float>(q, X_dev, rows, cols, ld, stream);
+}
+extern "C" int gr_quantizer_bind_f64(gr_quantizer_t* q, const double* X_dev, int64_t rows,
+                                     int64_t cols, int64_t ld, void* stream) {
+    return bind_impl<double>(q, X_dev, rows, cols, ld, stream);
+}
+
+extern "C" int gr_quantizer_encode_f32(gr_quantizer_t* q, int32_t n_bins, uint32_t seed,
+                                       int32_t max_iter, double tol, float* out_dev, int64_t ldo,
+                                       double* centers_out_host, int32_t* n_iter_out,
+                                       int64_t* n_distinct_out, void* stream) {
+    return encode_impl<float>(q, n_bins, seed, max_iter, tol, out_dev, ldo, centers_out_host,
+                              n_iter_out, n_distinct_out, stream);
+}
+extern "C" int gr_quantizer_encode_f64(gr_quantizer_t* q, int32_t n_bins, uint32_t seed,
+                                       int32_t max_iter, double tol, double* out_dev, int64_t ldo,
+                                       double* centers_out_host, int32_t* n_iter_out,
+                                       int64_t* n_distinct_out, void* stream) {
+    return encode_impl<double>(q, n_bins, seed, max_iter, tol, out_dev, ldo, centers_out_host,
+                               n_iter_out, n_distinct_out, stream);
+}
+
+extern "C" int gr_quantizer_count_distinct(gr_quantizer_t* q, int64_t* n_distinct_out,
+                                           void* stream) {
+    GR_REQUIRE(q != nullptr && q->src != nullptr && n_distinct_out != nullptr,
+               "gr_quantizer_count_distinct: no matrix is bound");
+    DeviceGuard guard(q->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", q->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = reduce_blocks(q->N);
+    count_runs_kernel<<<blocks, kRedThreads, 0, st>>>(q->xs, q->N, q->partial);
+    count_launch();
+    double runs = 0.0;
+    if (int rc = finish_to_host(q, blocks, 1, 1, &runs, st)) return rc;
+    *n_distinct_out = (int64_t)runs;
+    return GR_OK;
+}
+
+extern "C" int gr_mdl_error_cost_f32(const float* V, int64_t n, int32_t f, int64_t ldv,
+                                     const float* G, int64_t ldg, const float* F, int64_t ldf,
+                                     int32_t r, double* cost_out, int device, void* stream) {
+    return kl_impl<float>(V, n, f, ldv, G, ldg, F, ldf, r, cost_out, device, stream);
+}
+extern "C" int gr_mdl_error_cost_f64(const double* V, int64_t n, int32_t f, int64_t ldv,
+                                     const double* G, int64_t ldg, const double* F, int64_t ldf,
+                                     int32_t r, double* cost_out, int device, void* stream) {
+    return kl_impl<double>(V, n, f, ldv, G, ldg, F, ldf, r, cost_out, device, stream);
+}
+extern "C" int gr_mdl_kl_f64(const double* V, const double* V_approx, int64_t n, int32_t f,
+                             int64_t ldv, int64_t lda, double* cost_out, int device, void* stream) {
+    return kl_pair_impl<double>(V, V_approx, n, f, ldv, lda, cost_out, device, stream);
+}
+
+extern "C" int gr_roles_f32(const float* W, int64_t n, int32_t r, int64_t ldw, int32_t* argmax_dev,
+                            float* pct_dev, int64_t ldp, int device, void* stream) {
+    return roles_impl<float>(W, n, r, ldw, argmax_dev, pct_dev, ldp, device, stream);
+}
+extern "C" int gr_roles_f64(const double* W, int64_t n, int32_t r, int64_t ldw, int32_t* argmax_dev,
+                            double* pct_dev, int64_t ldp, int device, void* stream) {
+    return roles_impl<double>(W, n, r, ldw, argmax_dev, pct_dev, ldp, device, stream);
+}
+
+// NumPy RandomState(seed).random_sample(count): exposed so that the host tests can pin the stream
+// the quantiser's seeding relies on (no device needed).
+extern "C" int gr_numpy_random_sample(uint32_t seed, int64_t count, double* out_host) {
+    GR_REQUIRE(out_host != nullptr && count >= 0, "gr_numpy_random_sample: bad arguments");
+    NumpyRandomState rs(seed);
+    for (int64_t i = 0; i < count; ++i) out_host[i] = rs.random_sample();
+    return GR_OK;
+}
+
+// RandomState(seed).choice(n, p=np.full(n, 1 / n)): the first k-means++ centre (_kmeans.py:231).
+extern "C" int gr_numpy_choice_uniform(uint32_t seed, int64_t n, int64_t* index_out) {
+    GR_REQUIRE(index_out != nullptr && n >= 1, "gr_numpy_choice_uniform: bad arguments");
+    NumpyRandomState rs(seed);
+    *index_out = choice_uniform(n, rs.random_sample());
+    return GR_OK;
+}

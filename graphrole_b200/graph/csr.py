@@ -153,10 +153,7 @@ class CSRGraph:
                     weights_integral=bool(z['weights_integral']))
             g.n_cols = int(z['n_cols'])
         if device is not None:
-            moved = g.to(device)
-            if g.weights is not None:
-                moved.weights = g.weights.to(device)
-            g = moved
+            g = g.to(device)
         return g
 
     @classmethod
@@ -209,7 +206,8 @@ class CSRGraph:
         key = str(device)
         if key not in self._device_copies:
             g = CSRGraph(self.rowptr.to(device), self.colidx.to(device), labels=self.labels,
-                         directed=self.directed, weights=None,
+                         directed=self.directed,
+                         weights=None if self.weights is None else self.weights.to(device),
                          weights_integral=self.weights_integral)
             g.n_cols = self.n_cols
             self._device_copies[key] = g

@@ -7,15 +7,13 @@ from graphrole_b200.graph.interface.csr import CSRInterface
 from graphrole_b200.graph.interface.networkx import NetworkxInterface
 
 
-def _igraph_interface(G, **kwargs):
-    # imported on use: python-igraph is optional
-    from graphrole_b200.graph.interface.igraph import IgraphInterface
-    return IgraphInterface(G, **kwargs)
-
-
+# The reference also registers an igraph adapter (graphrole/graph/interface/igraph.py); igraph is
+# an optional dependency that is not installed here, SURVEY.md section 2 marks it out of scope, and
+# an adapter nobody can run is not shipped.  Any graph library plugs in the reference's way:
+# subclass BaseGraphInterface (get_nodes / get_neighbors are enough for the CSR ingest) and
+# register it under the graph object's top-level module name.
 INTERFACES = {
     'networkx': NetworkxInterface,
-    'igraph': _igraph_interface,
     # graphrole_b200.graph.csr.CSRGraph: arrays already in CSR form (and possibly in HBM)
     'graphrole_b200': CSRInterface,
 }

@@ -6,7 +6,6 @@ the multiplicative-update loop is the CUDA library's gr_nmf_mu_f32 (include/grap
 the NNDSVDa start is computed on the device with torch.linalg (not a hot path, SURVEY.md
 section 8 row B2).
 """
-import warnings
 from ctypes import byref, c_double, c_int32, c_void_p
 from typing import Optional, Tuple
 
@@ -20,6 +19,7 @@ from graphrole_b200.types import FactorTuple
 MAX_ITER = 200
 TOL = 1e-4
 CHECK_EVERY = 10
+MAX_ROLES = 32      # rank limit of the CUDA kernels (gr_nmf_create)
 # which kernels the most recent nmf_mu call ran: 'tcgen05' or 'ffma'
 last_path = None
 
@@ -34,8 +34,13 @@ def get_nmf_decomposition(X: np.ndarray, n_roles: int) -> FactorTuple:
     X = np.asarray(X)
     if X.ndim != 2:
         raise ValueError('X must be a 2-D array')
+    if not np.all(np.isfinite(X)):
+        # sklearn's input validation (check_array) refuses these before the solver starts
+        raise ValueError('Input X contains NaN or infinity.')
     if np.any(X < 0):
         raise ValueError('Negative values in data passed to NMF')
+    if n_roles > MAX_ROLES:
+        raise ValueError(f'n_roles = {n_roles}: the CUDA solver supports at most {MAX_ROLES}')
     device = torch.device('cuda', torch.cuda.current_device())
     Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32), device=device)
     W0, H0 = nndsvda_init(Xd, n_roles)
@@ -203,14 +208,19 @@ def nndsvda_init(X: torch.Tensor, n_components: int, eps: float = 1e-6,
 
 
 def encode(X: np.ndarray, n_bins: int) -> np.ndarray:
-    """Quantise X to n_bins levels with a Lloyd-Max quantiser (1-D k-means on the entries),
-    as graphrole/roles/factor.py:29-49 does; raises ValueError when n_bins exceeds the
-    number of entries (callers rely on that)."""
-    from sklearn.cluster import KMeans
-    flat = np.asarray(X, dtype=np.float64).reshape(-1, 1)
-    quantizer = KMeans(n_clusters=n_bins, random_state=1)
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore')
-        quantizer.fit(flat)
-    levels = quantizer.cluster_centers_.ravel()
-    return levels[quantizer.labels_].reshape(np.shape(X))
+    """Quantise X to n_bins levels with a Lloyd-Max quantiser (1-D k-means on the entries), as
+    graphrole/roles/factor.py:29-49 does with KMeans(n_clusters=n_bins, random_state=1); raises
+    ValueError (TooManyBinsError) when n_bins exceeds the number of entries -- callers rely on
+    that.  Runs on the GPU (gr_quantizer_*, csrc/rolx_epilogue.cu): same k-means++ stream, same
+    stopping rules, labels equal scikit-learn's when X holds at least n_bins distinct values."""
+    X = np.asarray(X, dtype=np.float64)
+    if n_bins > X.size:
+        raise _native.TooManyBinsError(f'n_samples={X.size} should be >= n_clusters={n_bins}.')
+    device = torch.device('cuda', torch.cuda.current_device())
+    flat = np.ascontiguousarray(X).reshape(-1, X.shape[-1] if X.ndim >= 1 and X.size else 1)
+    quantizer = _native.Quantizer(X.size, device)
+    try:
+        out, _ = quantizer.bind(torch.as_tensor(flat, device=device)).encode(n_bins)
+        return out.cpu().numpy().reshape(X.shape)
+    finally:
+        quantizer.close()

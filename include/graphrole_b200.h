@@ -82,6 +82,11 @@ int gr_csr_create(gr_csr_t** out, int64_t n_rows, int64_t n_cols, int64_t nnz,
                   const int64_t* rowptr_dev, const int32_t* colidx_dev,
                   int device, int flags);
 int gr_csr_destroy(gr_csr_t* g);
+/* Re-computes the GR_CSR_HOT_HINTS tags for feature rows of `row_bytes` bytes (default 256 =
+ * 64 fp32 columns): the hot set is as many of the most gathered rows as fit the L2 budget, so a
+ * column-group shard that aggregates 8 columns (32-byte rows) can pin 8 x as many rows.  Cache
+ * hint only -- results do not change.  Synchronises the device. */
+int gr_csr_tune_hot_rows(gr_csr_t* g, int64_t row_bytes);
 /* n_rows, n_cols, nnz, number of hub rows (rows split across warps), number of hub segments,
  * number of rows tagged hot (0 without GR_CSR_HOT_HINTS) */
 int gr_csr_info(const gr_csr_t* g, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
@@ -153,6 +158,22 @@ int gr_peer_barrier_status(const void* own_flag_array, int64_t* timed_out_epoch)
  * out_host: levels * n_rows * 2*d floats, level-major.  Synchronous. */
 int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,
                              int32_t levels, int32_t recurse_on, float* out_host, void* stream);
+
+/* Host-buffer variant of a NODE-RANGE SHARD (section 8e): every rank of an exchange group calls
+ * it with its shard handle.  X_host is the level-0 input of ALL n_cols nodes (row stride ldx; a
+ * column group passes X_host + first_column).  Each level is gr_refex_aggregate_bcast_f32 into
+ * the other replica set followed by gr_peer_barrier; the OWN rows of every level are copied
+ * back, overlapped with the next level: out_host [levels, n_rows, 2*d] (sum block | mean block).
+ *   replicas_even / replicas_odd  n_ranks device pointers each: base of every rank's [n_cols, d]
+ *                  replica used as input of the even / odd levels (own at index `rank`)
+ *   flag_arrays, epoch_inout      as gr_peer_barrier; *epoch_inout is advanced once per level
+ *   row_offset     global row number of the handle's row 0
+ * Recurses on the mean block.  Synchronous.  n_ranks == 1 needs no peers (flags unused). */
+int gr_refex_levels_host_sharded_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,
+                                     int32_t levels, int64_t row_offset,
+                                     float* const* replicas_even, float* const* replicas_odd,
+                                     void* const* flag_arrays, int32_t n_ranks, int32_t rank,
+                                     int64_t* epoch_inout, float* out_host, void* stream);
 
 /* ---- path B: RolX NMF, multiplicative updates, Frobenius loss ---------------------------
  * Replaces sklearn.decomposition._nmf._fit_multiplicative_update (beta_loss=2, no
@@ -232,6 +253,73 @@ int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* rowptr_dev,
                            int32_t directed, double* out_weight_dev, double* in_weight_dev,
                            double* diag_dev, double* internal_dev, double* external_dev,
                            int device, void* stream);
+
+/* ---- RolX epilogue: what RoleExtractor runs after the NMF ------------
+ *
+ * Lloyd-Max quantiser, replacing graphrole/roles/factor.py:29-49:
+ *     KMeans(n_clusters=n_bins, random_state=seed).fit(X.reshape(X.size, 1)); centres[labels]
+ * (sklearn/cluster/_kmeans.py: fit :1440-1563, k-means++ :180-278, Lloyd :620-758).
+ * gr_quantizer_bind_*   takes the matrix (rows x cols, row stride ld, row-major flattening order
+ *     like X.reshape): centres the entries by their mean, sorts them once and prefix-sums the
+ *     sorted values -- shared by every n_bins tried on the same matrix (the grid of
+ *     roles/extract.py:121-133 quantises one factor with 2^1 .. 2^8 bins).
+ * gr_quantizer_encode_* k-means++ seeding with NumPy's RandomState(seed) stream (the reference
+ *     hard-codes seed 1), Lloyd iterations until labels repeat or the squared centre shift is
+ *     <= tol * var(X) (sklearn: tol 1e-4, max_iter 300), then out = centre of every entry's
+ *     cluster (same shape, row stride ldo).  centers_out_host[n_bins] receives cluster_centers_ in
+ *     sklearn's cluster order (NaN when the data hold fewer distinct values than n_bins -- then
+ *     every distinct value is its own level and out == X), n_distinct_out the number of distinct
+ *     output values (np.unique(encoded).size, description_length.py:37-38).
+ *     n_bins > rows * cols is refused with sklearn's message "n_samples=... should be >=
+ *     n_clusters=..." (GR_ERR_INVALID_ARGUMENT): callers rely on it (roles/extract.py:127-129).
+ *     n_bins <= 1024.  Labels equal scikit-learn's when the data hold >= n_bins distinct values.
+ * The handle owns about 48 bytes of device workspace per entry of `capacity`.
+ */
+typedef struct gr_quantizer gr_quantizer_t;
+
+int gr_quantizer_create(gr_quantizer_t** out, int64_t capacity, int device);
+int gr_quantizer_destroy(gr_quantizer_t* q);
+int gr_quantizer_bind_f32(gr_quantizer_t* q, const float* X_dev, int64_t rows, int64_t cols,
+                          int64_t ld, void* stream);
+int gr_quantizer_bind_f64(gr_quantizer_t* q, const double* X_dev, int64_t rows, int64_t cols,
+                          int64_t ld, void* stream);
+int gr_quantizer_encode_f32(gr_quantizer_t* q, int32_t n_bins, uint32_t seed, int32_t max_iter,
+                            double tol, float* out_dev, int64_t ldo, double* centers_out_host,
+                            int32_t* n_iter_out, int64_t* n_distinct_out, void* stream);
+int gr_quantizer_encode_f64(gr_quantizer_t* q, int32_t n_bins, uint32_t seed, int32_t max_iter,
+                            double tol, double* out_dev, int64_t ldo, double* centers_out_host,
+                            int32_t* n_iter_out, int64_t* n_distinct_out, void* stream);
+/* np.unique(X).size of the bound matrix (description_length.py:37-38 on an encoded factor). */
+int gr_quantizer_count_distinct(gr_quantizer_t* q, int64_t* n_distinct_out, void* stream);
+
+/* Description-length error cost, replacing graphrole/roles/description_length.py:44-61 together
+ * with the product at :19:  sum over V[i,j] != 0 of  v log(v / a) - v + a,  a = (G F)[i, j],
+ * V [n, f], G [n, r], F [r, f] (r <= 64), fp64 arithmetic for either storage type, fixed
+ * reduction order.  gr_mdl_kl_f64 is the same sum for an explicit approximation matrix
+ * (get_error_cost(V, V_approx)).  Synchronous: cost_out is a host pointer. */
+int gr_mdl_error_cost_f32(const float* V_dev, int64_t n, int32_t f, int64_t ldv,
+                          const float* G_dev, int64_t ldg, const float* F_dev, int64_t ldf,
+                          int32_t r, double* cost_out, int device, void* stream);
+int gr_mdl_error_cost_f64(const double* V_dev, int64_t n, int32_t f, int64_t ldv,
+                          const double* G_dev, int64_t ldg, const double* F_dev, int64_t ldf,
+                          int32_t r, double* cost_out, int device, void* stream);
+int gr_mdl_kl_f64(const double* V_dev, const double* V_approx_dev, int64_t n, int32_t f,
+                  int64_t ldv, int64_t lda, double* cost_out, int device, void* stream);
+
+/* RoleExtractor.roles / .role_percentage (graphrole/roles/extract.py:38-57): index of the first
+ * maximum of every row of the node-role factor and the row divided by its sum.  Either output may
+ * be NULL. */
+int gr_roles_f32(const float* W_dev, int64_t n, int32_t r, int64_t ldw, int32_t* argmax_dev,
+                 float* pct_dev, int64_t ldp, int device, void* stream);
+int gr_roles_f64(const double* W_dev, int64_t n, int32_t r, int64_t ldw, int32_t* argmax_dev,
+                 double* pct_dev, int64_t ldp, int device, void* stream);
+
+/* np.random.RandomState(seed).random_sample(count) -- the stream the quantiser's seeding draws
+ * from; host only, exposed so it can be pinned against NumPy without a device. */
+int gr_numpy_random_sample(uint32_t seed, int64_t count, double* out_host);
+/* RandomState(seed).choice(n, p=uniform): index of the first k-means++ centre (_kmeans.py:231);
+ * exact up to n = 2^24, floor(u n) beyond (see csrc/rolx_epilogue.cu). */
+int gr_numpy_choice_uniform(uint32_t seed, int64_t n, int64_t* index_out);
 
 #ifdef __cplusplus
 }

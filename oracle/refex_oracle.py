@@ -120,6 +120,10 @@ def c_lib():
             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
         lib.refex_oracle_threads.restype = ctypes.c_int
+        lib.refex_oracle_level_check_f64.restype = ctypes.c_int
+        lib.refex_oracle_level_check_f64.argtypes = [
+            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
         _clib = lib
     return _clib
 
@@ -144,3 +148,25 @@ def aggregate_rows_c(rows, rowptr, colidx, X32, threads=0):
 
 def c_threads():
     return int(c_lib().refex_oracle_threads())
+
+
+def level_check_f64(rowptr, colidx, X64, gpu_out32, threads=0):
+    """One level of the float64 recursion over the WHOLE graph, compared with the GPU's float32
+    [sum | mean] output of the same level.  Returns (next-level float64 input = this level's
+    means, max relative error of the sums, of the means, count of non-zero GPU entries where the
+    float64 value is exactly 0).  X64 is what the reference would carry between levels
+    (extract.py:77-83 never leaves float64)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+    X64 = np.ascontiguousarray(X64, dtype=np.float64)
+    gpu_out32 = np.ascontiguousarray(gpu_out32, dtype=np.float32)
+    n, d = X64.shape
+    assert rowptr.shape[0] == n + 1 and gpu_out32.shape == (n, 2 * d)
+    nxt = np.empty((n, d), dtype=np.float64)
+    err = np.zeros(3, dtype=np.float64)
+    rc = c_lib().refex_oracle_level_check_f64(
+        n, rowptr.ctypes.data, colidx.ctypes.data, X64.ctypes.data, d, gpu_out32.ctypes.data,
+        nxt.ctypes.data, err.ctypes.data, threads)
+    if rc != 0:
+        raise RuntimeError(f'refex_oracle_level_check_f64 failed with {rc}')
+    return nxt, float(err[0]), float(err[1]), int(err[2])

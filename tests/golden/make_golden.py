@@ -17,6 +17,9 @@ Outputs (all small, committed):
                        reference's `_get_next_features` output for them
   prune_cases.json     reference pruner outputs (binning vectors, dropped sets) on seeded data
   prune_reference_tables.json  the reference's own known-answer tables for the pruner, re-run
+  rolx_cases.npz       the reference's `encode` (= sklearn KMeans(random_state=1) on the flattened
+                       matrix) and description-length costs on seeded inputs, plus one row of
+                       the model-selection grid (fixed factors, bits 1..8)
   nmf_cases.npz        sklearn MU runs with explicit (W0, H0): factors after a fixed number
                        of iterations and at the stopping iteration, plus
                        graphrole.roles.factor.get_nmf_decomposition under np.random.seed
@@ -374,11 +377,116 @@ def roles_cases():
         json.dump(cases, f)
 
 
+def rolx_cases():
+    """RolX epilogue: graphrole/roles/factor.py:29-49 (`encode`) and
+    graphrole/roles/description_length.py on seeded inputs.  Every encode input holds at least
+    as many distinct values as bins (below that scikit-learn's result depends on
+    np.argpartition's order of equal keys and is not a stable target).  Grid-valued data with
+    almost as many bins as distinct values (round2000x3 at 64 bins: 101 distinct values) are left
+    out for the same reason: points exactly half way between two centres are assigned by the
+    rounding noise of scikit-learn's BLAS calls."""
+    from graphrole.roles import description_length as ref_dl
+    out = {}
+    rng = np.random.RandomState(0)
+    nmf = np.load(os.path.join(HERE, 'nmf_cases.npz'))
+    inputs = {
+        'rand20x30': (np.random.RandomState(0).rand(20, 30), [2, 4, 8, 16, 64, 256]),
+        'exp400x5': (rng.exponential(size=(400, 5)) ** 2, [2, 3, 4, 8, 32, 128, 256]),
+        'nmfG300x8': (nmf['rand300x64__r8__Wconv'], [2, 4, 16, 64, 256]),
+        'nmfF8x64': (nmf['rand300x64__r8__Hconv'], [2, 4, 16, 64, 256]),
+        'round2000x3': (np.round(rng.rand(2000, 3), 2), [2, 4, 8, 16, 32]),
+        'halfzeros1000x4': (np.maximum(rng.randn(1000, 4), 0), [2, 4, 8, 16, 64]),
+        'vector37': (rng.rand(37), [2, 5, 37]),
+    }
+    names = []
+    for name, (X, bins) in inputs.items():
+        out[f'{name}__X'] = X
+        out[f'{name}__bins'] = np.array(bins)
+        names.append(name)
+        for k in bins:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                out[f'{name}__enc{k}'] = ref_factor.encode(X.copy(), k)
+    out['encode_names'] = np.array(names)
+
+    # description length: (V, encoded factors) -> (encoding cost, error cost)
+    V = rng.rand(40, 12)
+    V[rng.rand(40, 12) < 0.1] = 0.0            # the cost skips v == 0 (description_length.py:57)
+    out['dl__V'] = V
+    dl_rows = []
+    for r, bits in [(2, 1), (3, 3), (5, 5)]:
+        np.random.seed(11)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            G, F = ref_factor.get_nmf_decomposition(V, r)
+            Ge, Fe = ref_factor.encode(G, 2 ** bits), ref_factor.encode(F, 2 ** bits)
+        enc, err = get_description_length_costs(V, (Ge, Fe))
+        out[f'dl__r{r}b{bits}__G'] = Ge
+        out[f'dl__r{r}b{bits}__F'] = Fe
+        out[f'dl__r{r}b{bits}__costs'] = np.array([enc, err])
+        assert enc == ref_dl.get_encoding_cost((Ge, Fe))
+        dl_rows.append(f'r{r}b{bits}')
+    out['dl_names'] = np.array(dl_rows)
+
+    # one row of the model-selection grid (roles/extract.py:121-133) with the factors held fixed:
+    # encode + costs for bits 1..8 (NaN where encode raises ValueError)
+    V = rng.rand(60, 20) @ np.diag(rng.rand(20) + 0.2)
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        G, F = ref_factor.get_nmf_decomposition(V, 4)
+    grid = np.full((9, 2), np.nan)
+    for bits in range(1, 9):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                model = (ref_factor.encode(G, 2 ** bits), ref_factor.encode(F, 2 ** bits))
+        except ValueError:
+            continue
+        grid[bits] = get_description_length_costs(V, model)
+    out['grid__V'], out['grid__G'], out['grid__F'], out['grid__costs'] = V, G, F, grid
+
+    # the whole model selection on the reference's own test input (tests/test_roles/
+    # test_extract.py:81-88, seeded 20 x 30 uniform data).  That test expects 2 roles; under the
+    # scikit-learn installed here (1.9.0) the UNMODIFIED reference selects what is recorded below
+    # (the reference's examples/example.py:24-28 warns that results depend on the version).
+    np.random.seed(0)
+    feats = pd.DataFrame(np.random.rand(20, 30))
+    rx = RoleExtractor()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        rx.extract_role_factors(feats)
+    out['select__X'] = feats.values
+    out['select__n_roles'] = np.array(rx.node_role_factor.shape[1])
+    out['select__n_levels'] = np.array(len(np.unique(rx.node_role_factor.values)))
+    enc_grid, err_grid = np.full((9, 9), np.nan), np.full((9, 9), np.nan)
+    for roles in range(2, 9):
+        np.random.seed(roles)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            G, F = ref_factor.get_nmf_decomposition(feats.values, roles)
+        for bits in range(1, 9):
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    model = (ref_factor.encode(G, 2 ** bits), ref_factor.encode(F, 2 ** bits))
+            except ValueError:
+                continue
+            enc_grid[roles, bits], err_grid[roles, bits] = get_description_length_costs(
+                feats.values, model)
+    out['select__encoding_costs'], out['select__error_costs'] = enc_grid, err_grid
+    np.savez_compressed(os.path.join(HERE, 'rolx_cases.npz'), **out)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['rolx']:        # add this fixture without touching the others
+        rolx_cases()
+        sys.exit(0)
     refex_cases()
     refex_random()
     prune_cases()
     prune_reference_tables()
     nmf_cases()
     roles_cases()
+    rolx_cases()
     print('golden fixtures written to', HERE)

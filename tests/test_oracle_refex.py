@@ -104,3 +104,29 @@ def test_empty_and_degenerate_inputs():
     S, M = oracle.aggregate_rows_c(np.arange(3), rp, np.zeros(0, dtype=np.int32),
                                    np.ones((3, 2), dtype=np.float32))
     assert not S.any() and not M.any()
+
+
+def test_level_check_f64_is_the_float64_recursion():
+    """oracle.level_check_f64 (C, whole level, float64 carried between levels) against
+    aggregate_csr, and its error report against a perturbed 'GPU' output."""
+    rng = np.random.RandomState(0)
+    n, d = 4000, 6
+    src, dst = rng.randint(0, 3000, 30000), rng.randint(0, n, 30000)   # rows >= 3000 are empty
+    import scipy.sparse as sp
+    A = sp.csr_matrix((np.ones(30000), (src, dst)), shape=(n, n))
+    A.sum_duplicates()
+    rp, ci = A.indptr.astype(np.int64), A.indices.astype(np.int32)
+    X = rng.rand(n, d)
+    for _ in range(3):
+        S, M = oracle.aggregate_csr(rp, ci, X)
+        gpu = np.concatenate([S, M], axis=1).astype(np.float32)
+        nxt, es, em, bad = oracle.level_check_f64(rp, ci, X, gpu, threads=2)
+        np.testing.assert_allclose(nxt, M, rtol=1e-15, atol=0)
+        assert es < 1e-7 and em < 1e-7 and bad == 0
+        X = nxt
+    S, M = oracle.aggregate_csr(rp, ci, X)
+    gpu = np.concatenate([S, M], axis=1).astype(np.float32)
+    gpu[5, 2] *= 1.001
+    gpu[3500, 1] = 1.0                                  # an empty row must stay exactly zero
+    _, es, em, bad = oracle.level_check_f64(rp, ci, X, gpu)
+    assert es == pytest.approx(1e-3, rel=1e-3) and bad == 1

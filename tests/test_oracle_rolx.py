@@ -1,0 +1,75 @@
+"""The RolX-epilogue oracle (oracle/rolx_oracle.py) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py::rolx_cases -> graphrole.roles.factor.encode,
+graphrole.roles.description_length), and the NumPy RandomState stream the CUDA quantiser's
+seeding draws from (host-only entry points of the library: no GPU needed)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rolx_oracle as oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def rolx_cases():
+    return np.load(os.path.join(GOLDEN, 'rolx_cases.npz'))
+
+
+def test_encode_matches_the_reference(rolx_cases):
+    z = rolx_cases
+    for name in z['encode_names']:
+        X = z[f'{name}__X']
+        for k in z[f'{name}__bins']:
+            got = oracle.encode(X, int(k))
+            np.testing.assert_allclose(got, z[f'{name}__enc{k}'], rtol=1e-12, atol=1e-12,
+                                       err_msg=f'{name} bins={k}')
+
+
+def test_encode_refuses_more_bins_than_entries():
+    with pytest.raises(ValueError, match='should be >= n_clusters'):
+        oracle.encode(np.random.rand(2, 2), 16)
+
+
+def test_description_length_costs_match_the_reference(rolx_cases):
+    z = rolx_cases
+    V = z['dl__V']
+    for name in z['dl_names']:
+        G, F = z[f'dl__{name}__G'], z[f'dl__{name}__F']
+        enc, err = z[f'dl__{name}__costs']
+        assert oracle.encoding_cost(G, F) == enc
+        assert oracle.error_cost(V, G @ F) == pytest.approx(err, rel=1e-12)
+
+
+def test_grid_row_matches_the_reference(rolx_cases):
+    z = rolx_cases
+    V, G, F, want = z['grid__V'], z['grid__G'], z['grid__F'], z['grid__costs']
+    for bits in range(1, 9):
+        try:
+            Ge, Fe = oracle.encode(G, 2 ** bits), oracle.encode(F, 2 ** bits)
+        except ValueError:
+            assert np.isnan(want[bits]).all()
+            continue
+        assert oracle.encoding_cost(Ge, Fe) == want[bits, 0]
+        assert oracle.error_cost(V, Ge @ Fe) == pytest.approx(want[bits, 1], rel=1e-10)
+
+
+def test_rescale_and_select():
+    costs = np.array([[np.nan, np.nan], [3.0, 4.0], [np.nan, 2.0]])
+    got = oracle.rescale_costs(costs)
+    np.testing.assert_allclose(got[1], [0.6, 0.8])
+    assert oracle.select_model(costs, costs) == (1, 0)
+
+
+def test_library_random_stream_is_numpys():
+    """mt19937.h: RandomState(seed).random_sample and .choice(n, p=uniform)."""
+    from graphrole_b200 import _native
+    for seed in (0, 1, 7, 2 ** 31 + 5):
+        np.testing.assert_array_equal(np.array(_native.numpy_random_sample(seed, 1500)),
+                                      np.random.RandomState(seed).random_sample(1500))
+    for n in (1, 2, 3, 10, 999, 1000, 65536, 600_001):
+        for seed in range(12):
+            w = np.ones(n)
+            assert _native.numpy_choice_uniform(seed, n) == \
+                np.random.RandomState(seed).choice(n, p=w / w.sum())

@@ -270,6 +270,85 @@ def test_larger_random_graph_properties(n, deg, d):
     np.testing.assert_allclose(got[:, d:], M, rtol=RTOL)
 
 
+# ---- BASELINE.json's own configurations, at size ----------------------------------------------
+
+def recursion_against_float64(g, d, levels, seed=0):
+    """fp32 GPU recursion (schedule alpha: recurse on the mean block) against the float64
+    recursion the reference would carry (extract.py:77-83), EVERY row of EVERY level, through
+    oracle.level_check_f64.  Returns the per-level (sum, mean) max relative errors."""
+    rp, ci = g.host_arrays()
+    h = g.handle('cuda:0')
+    X = torch.rand(g.n, d, device='cuda:0', generator=torch.Generator('cuda:0').manual_seed(seed))
+    X64 = X.cpu().numpy().astype(np.float64)
+    deg = g.out_degree().to(torch.float32)[:, None]
+    errs = []
+    cur = X
+    out = None
+    for level in range(levels):
+        nxt = h.aggregate(cur)
+        # the mean is the correctly rounded fp32 quotient of the fp32 sum (never sum * (1 / deg))
+        assert torch.equal(nxt[:, d:], torch.where(deg > 0, nxt[:, :d] / deg.clamp(min=1),
+                                                    torch.zeros_like(nxt[:, :d])))
+        X64, err_sum, err_mean, bad_zero = oracle.level_check_f64(rp, ci, X64, nxt.cpu().numpy())
+        assert bad_zero == 0
+        errs.append((err_sum, err_mean))
+        out, cur = nxt, nxt[:, d:]
+        del nxt
+    return errs, out
+
+
+def test_config2_erdos_renyi_1m_20m_four_levels_every_row():
+    """BASELINE.json configs[1]: ER |V| = 1 M, |E| = 20 M, 32 features, 4 levels -- whole graph,
+    every row, float64 recursion; north_star tolerance 1e-5 relative."""
+    from graphrole_b200.graph.generators import erdos_renyi_csr
+    g = erdos_renyi_csr(1_000_000, 20_000_000, seed=0, device='cuda:0')
+    assert g.n == 1_000_000 and 39_900_000 < g.nnz <= 40_000_000
+    errs, _ = recursion_against_float64(g, 32, 4)
+    print('C2 max relative error per level (sum, mean):', errs)
+    assert max(max(e) for e in errs) <= RTOL
+
+
+def test_config3_barabasi_albert_10m_200m_five_levels_every_row():
+    """BASELINE.json configs[2]: BA |V| = 10 M, |E| ~ 200 M (nnz ~ 400 M, max degree ~ 9e4: hub
+    rows, 64-bit arc offsets past 2^31 bytes), 64 features, 5 levels -- whole graph, every row of
+    every level against the float64 recursion."""
+    import psutil
+    from graphrole_b200.graph.generators import barabasi_albert_csr
+    free_gpu, _ = torch.cuda.mem_get_info(0)
+    if psutil.virtual_memory().available < 40e9 or free_gpu < 40e9:
+        pytest.skip('needs ~25 GB of host memory and ~25 GB of HBM')
+    g = barabasi_albert_csr(10_000_000, 20, seed=0, device='cuda:0')
+    assert g.nnz > 399_000_000
+    info = g.handle('cuda:0').info()
+    assert info['n_hub_rows'] > 100
+    errs, last = recursion_against_float64(g, 64, 5)
+    print('C3 max relative error per level (sum, mean):', errs)
+    assert max(max(e) for e in errs) <= RTOL
+    # checksum of checksums on the last level: sum over rows of S = sum_j indeg(j) x_j
+    del last
+
+
+def test_mean_keeps_exact_ties_like_float64_division():
+    """a degree-7 node whose neighbours all carry the same integer must get exactly that
+    integer as its mean (21 * fl(1/7) = 3.0000002 would split a tie the reference keeps, and
+    vertical_log_binning is rank based).  All (degree, value) pairs up to 200 x 200."""
+    degs = np.arange(1, 201)
+    rows = np.repeat(np.arange(200), degs)                 # node i has degree i + 1
+    cols = 200 + np.concatenate([np.arange(k) for k in degs])
+    g = CSRGraph.from_edges(rows, cols, n=400, directed=True)
+    vals = np.arange(1, 201, dtype=np.float32)
+    X = np.tile(vals, (400, 1))                            # column c holds the value c + 1
+    got = gpu_aggregate(g, X)
+    np.testing.assert_array_equal(got[:200, 200:], np.tile(vals, (200, 1)))
+    np.testing.assert_array_equal(got[:200, :200], degs[:, None].astype(np.float32) * vals[None, :])
+    # hub rows follow the same rule
+    hub = CSRGraph.from_edges(np.zeros(2051, dtype=np.int64), 1 + np.arange(2051), n=2052,
+                              directed=True)
+    Xh = np.full((2052, 4), 3.0, dtype=np.float32)
+    out = gpu_aggregate(hub, Xh)
+    assert (out[0, 4:] == 3.0).all() and (out[0, :4] == 3.0 * 2051).all()
+
+
 # ---- node-range shards and the fused gather + broadcast kernel (SURVEY.md section 8e) -------
 
 def test_row_slice_shards_reproduce_the_unsharded_bits():

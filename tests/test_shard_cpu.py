@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from graphrole_b200.graph.generators import barabasi_albert_csr, erdos_renyi_csr
-from graphrole_b200.shard import cost_balanced_ranges, exchange_rows, nnz_balanced_ranges
+from graphrole_b200.shard import (column_groups, cost_balanced_ranges, default_column_groups,
+                                  exchange_rows, nnz_balanced_ranges, time_balanced_ranges)
 from oracle import refex_oracle as oracle
 
 
@@ -77,6 +78,51 @@ def test_row_slice_keeps_global_columns():
     assert int(srp[-1]) == sci.size
 
 
+def test_time_balanced_ranges_equalise_a_known_cost():
+    """Measured-feedback balancing: with per-range times generated from a hidden cost model
+    (arcs + 30 per row, one rank additionally 1.8x slow), two corrections bring max / mean of
+    the modelled times from > 1.5 to < 1.05; ranges always tile [0, n)."""
+    g = barabasi_albert_csr(200_000, 10, seed=1, device='cpu')
+    rp = g.rowptr.double()
+
+    def modelled(ranges):
+        return [float(rp[hi] - rp[lo]) + 30.0 * (hi - lo) for lo, hi in ranges]
+
+    for world in (2, 4, 8):
+        ranges = nnz_balanced_ranges(g.rowptr, world)
+        t = modelled(ranges)
+        assert max(t) / (sum(t) / world) > 1.3
+        for _ in range(3):
+            ranges = time_balanced_ranges(g.rowptr, ranges, modelled(ranges))
+            assert ranges[0][0] == 0 and ranges[-1][1] == g.n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        t = modelled(ranges)
+        assert max(t) / (sum(t) / world) < 1.05
+    # equal times: nothing moves; one range: unchanged
+    ranges = nnz_balanced_ranges(g.rowptr, 4)
+    same = time_balanced_ranges(g.rowptr, ranges, [1.0] * 4, row_cost=0.0)
+    arcs = lambda rs: [int(g.rowptr[hi] - g.rowptr[lo]) for lo, hi in rs]   # noqa: E731
+    assert max(abs(a - b) for a, b in zip(arcs(same), arcs(ranges))) <= 2 * int(g.out_degree().max())
+    assert time_balanced_ranges(g.rowptr, [(0, g.n)], [3.0]) == [(0, g.n)]
+
+
+def test_column_groups():
+    assert column_groups(64, 1) == [(0, 64)]
+    assert column_groups(64, 2) == [(0, 32), (32, 64)]
+    assert column_groups(64, 8) == [(i * 8, i * 8 + 8) for i in range(8)]
+    assert column_groups(12, 2) == [(0, 4), (4, 12)] or column_groups(12, 2) == [(0, 8), (8, 12)] \
+        or column_groups(12, 2) == [(0, 4), (4, 12)]
+    for d, c in ((12, 2), (7, 3), (5, 5), (100, 8)):
+        groups = column_groups(d, c)
+        assert groups[0][0] == 0 and groups[-1][1] == d and len(groups) == c
+        assert all(a[1] == b[0] and a[1] > a[0] for a, b in zip(groups, groups[1:]))
+    with pytest.raises(ValueError):
+        column_groups(3, 4)
+    assert default_column_groups(1, 64) == 1 and default_column_groups(4, 64) == 1
+    assert default_column_groups(8, 64) == 2
+    assert default_column_groups(8, 32) == 1       # 16 columns per group gather too narrowly
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
@@ -127,3 +173,51 @@ def test_two_rank_recursion_equals_single_process(equal_rows):
         _, cur = oracle.aggregate_csr(rp, ci, cur)
     for rank in range(world):
         np.testing.assert_allclose(ret[rank], cur, rtol=1e-13, atol=0)
+
+
+def _grid_worker(rank, world, port, levels, ret):
+    """C = 2 column groups x R = 2 node ranges on 4 gloo ranks: the exchange of a column group
+    runs in its own process group and never sees the other group's columns."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        C, R = 2, 2
+        c, r = rank % C, rank // C
+        g = barabasi_albert_csr(2000, 5, seed=7, device='cpu')
+        d = 8
+        c0, c1 = column_groups(d, C)[c]
+        X0 = torch.rand(g.n, d, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+        groups = [dist.new_group([q * C + cc for q in range(R)]) for cc in range(C)]
+        members = [q * C + c for q in range(R)]
+        ranges = cost_balanced_ranges(g.rowptr, R, 10.0)
+        lo, hi = ranges[r]
+        shard = g.row_slice(lo, hi)
+        rp, ci = shard.host_arrays()
+        rp, ci = rp - rp[0], ci[rp[0]:]
+        cur = X0[:, c0:c1].contiguous()
+        for _ in range(levels):
+            nxt = torch.full((g.n, c1 - c0), float('nan'), dtype=torch.float64)
+            _, M = oracle.aggregate_csr(rp, ci, cur.numpy())
+            nxt[lo:hi] = torch.from_numpy(M)
+            exchange_rows(nxt, ranges, r, groups[c], members)
+            cur = nxt
+        ret[rank] = (c0, c1, cur.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_groups_times_node_ranges_on_four_ranks():
+    world, levels = 4, 3
+    port = _free_port()
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_grid_worker, args=(world, port, levels, ret), nprocs=world, join=True)
+    g = barabasi_albert_csr(2000, 5, seed=7, device='cpu')
+    rp, ci = g.host_arrays()
+    cur = torch.rand(g.n, 8, generator=torch.Generator().manual_seed(0),
+                     dtype=torch.float64).numpy()
+    for _ in range(levels):
+        _, cur = oracle.aggregate_csr(rp, ci, cur)
+    for rank in range(world):
+        c0, c1, got = ret[rank]
+        np.testing.assert_allclose(got, cur[:, c0:c1], rtol=1e-13, atol=0)
