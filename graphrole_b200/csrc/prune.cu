@@ -352,10 +352,13 @@ extern "C" int gr_prune_pairwise_gap_i32(gr_pruner_t* h, const int32_t* bins_dev
     const int T = ceil_div(d, 4);
     const int n_pair_tiles = T * (T + 1) / 2;
     if (h->pair_tiles_for_d != d) {
-        GR_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(h->pair_tiles);
-        h->pair_tiles = nullptr;
-        GR_CUDA_TRY(cudaMalloc((void**)&h->pair_tiles, (size_t)n_pair_tiles * sizeof(int2)));
+        // the table buffer is sized once for d = 1024: re-filling it is a stream-ordered kernel,
+        // no allocation and no synchronisation per call (d changes with every generation)
+        if (!h->pair_tiles) {
+            constexpr int kMaxT = 256;
+            GR_CUDA_TRY(cudaMalloc((void**)&h->pair_tiles,
+                                   (size_t)(kMaxT * (kMaxT + 1) / 2) * sizeof(int2)));
+        }
         h->pair_tiles_for_d = d;
         pair_tile_table_kernel<<<dim3(T, ceil_div(T, 64)), 64, 0, st>>>(h->pair_tiles, T);
         count_launch();

@@ -591,10 +591,25 @@ extern "C" int gr_refex_levels_host_sharded_f32(
     }
 
     float* const* reps[2] = {replicas_even, replicas_odd};
-    GR_CUDA_TRY(cudaMemcpy2DAsync(reps[0][rank], (size_t)d * sizeof(float), X_host,
-                                  (size_t)ldx * sizeof(float), (size_t)d * sizeof(float),
-                                  (size_t)g->n_cols, cudaMemcpyHostToDevice, st));
     const size_t row_bytes = (size_t)d * sizeof(float);
+    // Level-0 input: every rank copies only ITS rows of X from the host (one PCIe link each) and
+    // then pushes them into the peers' replicas over NVLink -- an all-gather of X0 that moves
+    // n_cols * d * 4 / n_ranks bytes per PCIe link instead of all of it.
+    if (g->n_rows > 0) {
+        float* own = reps[0][rank] + (size_t)row_offset * d;
+        GR_CUDA_TRY(cudaMemcpy2DAsync(own, row_bytes, X_host + (size_t)row_offset * ldx,
+                                      (size_t)ldx * sizeof(float), row_bytes, (size_t)g->n_rows,
+                                      cudaMemcpyHostToDevice, st));
+        for (int p = 0; p < n_ranks; ++p)
+            if (p != rank)
+                GR_CUDA_TRY(cudaMemcpyAsync(reps[0][p] + (size_t)row_offset * d, own,
+                                            (size_t)g->n_rows * row_bytes, cudaMemcpyDeviceToDevice,
+                                            st));
+    }
+    if (n_ranks > 1) {
+        *epoch_inout += 1;
+        if (int rc = gr_peer_barrier(flag_arrays, n_ranks, rank, *epoch_inout, 0.0, st)) return rc;
+    }
     const size_t out_pitch = 2 * row_bytes;
     const size_t level_floats = (size_t)g->n_rows * 2 * (size_t)d;
     for (int l = 0; l < levels; ++l) {

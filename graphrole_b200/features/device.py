@@ -72,7 +72,10 @@ class DeviceRecursiveFeatureExtractor:
         self._feature_group_thresh = 0
         self._names: List[str] = []                    # all retained columns, in frame order
         self._columns: Dict[str, torch.Tensor] = {}    # name -> fp32 [n]
-        self._bins: Dict[str, torch.Tensor] = {}       # name -> int32 [n] (binning is per column)
+        # binned columns of the working set, column-major and CONTIGUOUS in `_names` order (row k
+        # of the buffer = column _names[k]): the pairwise kernel reads them in place, a
+        # generation's candidates are binned straight into the rows behind the retained ones
+        self._bins_buf: Optional[torch.Tensor] = None
         # values of every feature ever recorded as retained: a later generation may prune it from
         # the working set, the reference still reports it (its _final_features keeps the values)
         self._final_values: Dict[str, torch.Tensor] = {}
@@ -133,23 +136,45 @@ class DeviceRecursiveFeatureExtractor:
     def _update(self, names: List[str], values: torch.Tensor) -> None:
         """Append a generation's candidates, prune, record what was retained
         (extract.py:121-142)."""
+        new = [(j, name) for j, name in enumerate(names) if name not in self._columns]
+        k_old = len(self._names)
+        need = k_old + len(names)
+        if self._bins_buf is None or self._bins_buf.shape[0] < need:
+            grown = torch.empty((max(need, 2 * k_old, 16), self.graph.n), dtype=torch.int32,
+                                device=self.device)
+            if self._bins_buf is not None and k_old:
+                grown[:k_old].copy_(self._bins_buf[:k_old])
+            self._bins_buf = grown
         with self._timed('bin'):
-            bins = self._pruner.bin_columns(values)
-        for j, name in enumerate(names):
-            if name not in self._columns:                  # a re-derived name keeps its first values
-                self._columns[name] = values[:, j]
-                self._bins[name] = bins[j]
-                self._names.append(name)
+            if len(new) == len(names):
+                self._pruner.bin_columns(values, out=self._bins_buf[k_old:k_old + len(names)])
+            elif new:                                       # a re-derived name keeps its first values
+                idx = torch.tensor([j for j, _ in new], device=self.device)
+                self._pruner.bin_columns(values.index_select(1, idx).contiguous(),
+                                         out=self._bins_buf[k_old:k_old + len(new)])
+        for j, name in new:
+            self._columns[name] = values[:, j]
+            self._names.append(name)
         all_names = list(self._names)
         with self._timed('pairwise'):
-            stacked = torch.stack([self._bins[name] for name in all_names]).contiguous()
-            gaps = self._pruner.pairwise_gaps(stacked).cpu().numpy()
+            gaps = self._pruner.pairwise_gaps(self._bins_buf[:len(all_names)]).cpu().numpy()
         generations = {gen: dict.fromkeys(cols) for gen, cols in self._final_features.items()}
         pruner = _PrecomputedGapsPruner(generations, self._feature_group_thresh, gaps)
         redundant = set(pruner.prune_features(_Columns(all_names)))
-        for name in redundant:
-            self._names.remove(name)
-            del self._columns[name], self._bins[name]
+        if redundant:
+            with self._timed('compact'):
+                keep = [k for k, name in enumerate(all_names) if name not in redundant]
+                # rows only move towards the front: gather the kept rows behind the first removed
+                # one through a temporary (index_select never aliases its output)
+                first = next(k for k, name in enumerate(all_names) if name in redundant)
+                tail = [k for k in keep if k > first]
+                if tail:
+                    moved = self._bins_buf.index_select(
+                        0, torch.tensor(tail, device=self.device))
+                    self._bins_buf[first:first + len(tail)].copy_(moved)
+            for name in redundant:
+                self._names.remove(name)
+                del self._columns[name]
         # columns.difference(redundant): sorted unique names (extract.py:140)
         # and pandas' Index.difference returns the names unsorted when nothing at all was dropped
         retained = list(pd.Index(names).difference(list(redundant)))

@@ -159,20 +159,36 @@ class DeviceModelGrid:
     codebook sizes and the description-length error cost.  Only scalars reach the host until
     `model()` fetches the winning cell's factors."""
 
-    def __init__(self, V: np.ndarray, device: Optional[torch.device] = None):
-        V = np.asarray(V)
-        if V.ndim != 2:
-            raise ValueError('the feature matrix must be 2-D')
-        if not np.all(np.isfinite(V)):
-            raise ValueError('Input X contains NaN or infinity.')
-        if np.any(V < 0):
-            raise ValueError('Negative values in data passed to NMF')
-        self.device = device or _cuda_device()
-        self.V = torch.as_tensor(np.ascontiguousarray(V, dtype=np.float32), device=self.device)
+    def __init__(self, V, device: Optional[torch.device] = None):
+        if isinstance(V, torch.Tensor) and V.is_cuda:
+            # features already in HBM (e.g. DeviceRecursiveFeatureExtractor's output)
+            if V.dim() != 2:
+                raise ValueError('the feature matrix must be 2-D')
+            if not bool(torch.isfinite(V).all()):
+                raise ValueError('Input X contains NaN or infinity.')
+            if bool((V < 0).any()):
+                raise ValueError('Negative values in data passed to NMF')
+            self.device = V.device
+            self.V = V.to(torch.float32).contiguous()
+        else:
+            V = np.asarray(V)
+            if V.ndim != 2:
+                raise ValueError('the feature matrix must be 2-D')
+            if not np.all(np.isfinite(V)):
+                raise ValueError('Input X contains NaN or infinity.')
+            if np.any(V < 0):
+                raise ValueError('Negative values in data passed to NMF')
+            self.device = device or _cuda_device()
+            self.V = torch.as_tensor(np.ascontiguousarray(V, dtype=np.float32),
+                                     device=self.device)
         self.n, self.f = self.V.shape
         self._factors: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._quantizers: Dict[int, Tuple[_native.Quantizer, _native.Quantizer]] = {}
         self.n_fits = 0
+
+    @classmethod
+    def from_device(cls, V: torch.Tensor) -> 'DeviceModelGrid':
+        return cls(V)
 
     def factors(self, n_roles: int, refit: bool = False):
         if n_roles > factor.MAX_ROLES:

@@ -201,7 +201,7 @@ def nndsvda_init(X: torch.Tensor, n_components: int, eps: float = 1e-6,
         H[j] = scale * v
     W[W < eps] = 0
     H[H < eps] = 0
-    avg = X.double().mean()
+    avg = X.mean(dtype=torch.float64)       # fp64 accumulation without an fp64 copy of X
     W[W == 0] = avg
     H[H == 0] = avg
     return W.float().contiguous(), H.float().contiguous()

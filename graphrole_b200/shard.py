@@ -370,8 +370,8 @@ class ShardedRefex:
             self.sums = torch.empty((hi - lo, self.d), dtype=torch.float32, device=self.device)
 
     # ---- measured balancing ---------------------------------------------------------------
-    def autobalance(self, X0: torch.Tensor, levels: int, rounds: int = 3,
-                    tolerance: float = 1.05) -> List[dict]:
+    def autobalance(self, X0: torch.Tensor, levels: int, rounds: int = 4,
+                    tolerance: float = 1.02) -> List[dict]:
         """Time this rank's kernel on the real input, all-gather the times, re-cut the node
         ranges so that the predicted per-rank time is equal; stop when max / mean <= tolerance
         or after `rounds` corrections.  Every rank derives the same ranges from the same
@@ -379,13 +379,14 @@ class ShardedRefex:
         if self.R == 1:
             return []
         import torch.distributed as dist
+        best = None                                  # (slowest range's ms, ranges)
         for it in range(rounds + 1):
             events = []
             self.run_levels(X0, levels, events)            # first pass also warms everything up
             events = []
             self.run_levels(X0, levels, events)
             torch.cuda.synchronize()
-            mine = sum(a.elapsed_time(b) for a, b in events) / max(levels, 1)
+            mine = sum(ev[0].elapsed_time(ev[1]) for ev in events) / max(levels, 1)
             t = torch.zeros(self.world, device=self.device, dtype=torch.float64)
             t[self.rank] = mine
             dist.all_reduce(t)
@@ -395,6 +396,8 @@ class ShardedRefex:
                          for q in range(self.R)]
             self.balance_history.append({'ranges': list(self.ranges),
                                          'kernel_ms': [round(x, 4) for x in per_range]})
+            if best is None or max(per_range) < best[0]:
+                best = (max(per_range), list(self.ranges))
             mean = sum(per_range) / len(per_range)
             if it == rounds or max(per_range) <= tolerance * mean:
                 break
@@ -405,12 +408,21 @@ class ShardedRefex:
             self.ranges = new
             self._build_shard()
             self.balance = f'measured-time-balanced ranges ({it + 1} correction(s))'
+        if best is not None and best[1] != self.ranges:
+            # a correction that made the slowest rank slower (the time inside a range is not
+            # uniform: one hub row can carry a fixed cost) is not kept
+            self.ranges = best[1]
+            self._build_shard()
+            self.balance += ', best measured split kept'
         return self.balance_history
 
     # ---- the recursion -------------------------------------------------------------------
     def run_levels(self, X0: torch.Tensor, levels: int, events: Optional[list] = None):
         """X0: the [n, d_total] level-0 input (every rank holds it).  Returns the last level's
-        (sum rows, mean rows) of this rank: rows [lo_r, hi_r), columns [col_lo, col_hi)."""
+        (sum rows, mean rows) of this rank: rows [lo_r, hi_r), columns [col_lo, col_hi).  With the
+        fused exchange the mean rows are a VIEW of this rank's replica, which the peers overwrite
+        in their next run_levels: synchronise the ranks before any of them starts another call
+        if the views are still in use."""
         d = self.d
         cur = X0[:, self.col_lo:self.col_hi]
         last = None
@@ -438,8 +450,11 @@ class ShardedRefex:
                 self.handle.aggregate_bcast(cur, self.sums, self.peers.replica_ptrs(which), d, lo)
                 if events is not None:
                     e1.record()
-                    events.append((e0, e1))
                 self.peers.barrier()
+                if events is not None:
+                    e2 = torch.cuda.Event(enable_timing=True)
+                    e2.record()
+                    events.append((e0, e1, e2))       # kernel = e0..e1, barrier wait = e1..e2
                 cur = self.peers.replicas[which]
                 last = (self.sums, cur[lo:hi])
             else:
@@ -447,8 +462,11 @@ class ShardedRefex:
                 self.handle.aggregate_into(cur, self.sums, nxt[lo:hi])
                 if events is not None:
                     e1.record()
-                    events.append((e0, e1))
                 exchange_rows(nxt, self.ranges, self.r, self.group, self.members)
+                if events is not None:
+                    e2 = torch.cuda.Event(enable_timing=True)
+                    e2.record()
+                    events.append((e0, e1, e2))
                 cur = nxt
                 last = (self.sums, nxt[lo:hi])
         if self.peers is not None:

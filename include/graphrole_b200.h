@@ -161,12 +161,14 @@ int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int3
 
 /* Host-buffer variant of a NODE-RANGE SHARD (section 8e): every rank of an exchange group calls
  * it with its shard handle.  X_host is the level-0 input of ALL n_cols nodes (row stride ldx; a
- * column group passes X_host + first_column).  Each level is gr_refex_aggregate_bcast_f32 into
+ * column group passes X_host + first_column); every rank copies only its own rows of it over
+ * PCIe and pushes them to the peers' replicas over NVLink (the ranks' row ranges must tile
+ * [0, n_cols)).  Each level is gr_refex_aggregate_bcast_f32 into
  * the other replica set followed by gr_peer_barrier; the OWN rows of every level are copied
  * back, overlapped with the next level: out_host [levels, n_rows, 2*d] (sum block | mean block).
  *   replicas_even / replicas_odd  n_ranks device pointers each: base of every rank's [n_cols, d]
  *                  replica used as input of the even / odd levels (own at index `rank`)
- *   flag_arrays, epoch_inout      as gr_peer_barrier; *epoch_inout is advanced once per level
+ *   flag_arrays, epoch_inout      as gr_peer_barrier; *epoch_inout is advanced levels + 1 times
  *   row_offset     global row number of the handle's row 0
  * Recurses on the mean block.  Synchronous.  n_ranks == 1 needs no peers (flags unused). */
 int gr_refex_levels_host_sharded_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int32_t d,

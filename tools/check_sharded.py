@@ -86,6 +86,8 @@ def main():
             wide = full_ref[levels - 1]
             ok_w = torch.allclose(means, wide[lo:hi, d + c0:d + c1], rtol=2e-6, atol=0) and \
                 torch.allclose(sums, wide[lo:hi, c0:c1], rtol=2e-6, atol=0)
+            torch.cuda.synchronize()
+            dist.barrier()        # the peers overwrite the replicas in their next run_levels
             if not (ok_s and ok_m and ok_f and ok_w):
                 failures += 1
                 print(f'[rank {rank}] MISMATCH mode={mode}/{eng.exchange} C={C} levels={levels} '
@@ -99,6 +101,7 @@ def main():
             for _ in range(2):                          # twice: buffers and epochs are reused
                 outh.fill_(-1.0)
                 eng.run_levels_host(Xh, args.levels, outh)
+                dist.barrier()
                 for level in range(args.levels):
                     ref = ref_levels[level]
                     if not torch.equal(outh[level].to(device), ref[lo:hi]):
