@@ -516,7 +516,8 @@ def e2e_section(engine, X0, n, nnz, d, levels, dist, device, args):
     lo, hi = engine.ranges[engine.r]
     Xh = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
     Xh.copy_(X0)
-    outh = torch.empty((levels, hi - lo, 2 * engine.d), dtype=torch.float32, pin_memory=True)
+    shape = (levels, hi - lo, 2 * engine.d) if engine.R == 1 else (levels, 2, hi - lo, engine.d)
+    outh = torch.empty(shape, dtype=torch.float32, pin_memory=True)
     engine.run_levels_host(Xh, levels, outh)       # warm-up (allocates staging)
     e2e_steps = max(1, min(args.steps, 3))
     torch.cuda.synchronize()
@@ -527,7 +528,8 @@ def e2e_section(engine, X0, n, nnz, d, levels, dist, device, args):
         engine.run_levels_host(Xh, levels, outh)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / e2e_steps
-    h2d = n * engine.d * 4
+    # a node-range shard uploads only its own rows of X0 (the peers get them over NVLink)
+    h2d = (n if engine.R == 1 else hi - lo) * engine.d * 4
     d2h = levels * (hi - lo) * 2 * engine.d * 4
     if dist is not None:
         t = torch.tensor([dt, float(h2d), float(d2h)], device=device, dtype=torch.float64)
@@ -537,8 +539,9 @@ def e2e_section(engine, X0, n, nnz, d, levels, dist, device, args):
         dt, h2d, d2h = float(mx[0]), int(t[1]), int(t[2])
     # spot check: the last level that came back equals the device-resident result
     sums, means = engine.run_levels(X0, levels)
-    same = torch.equal(outh[levels - 1, :, :engine.d].to(device), sums) and \
-        torch.equal(outh[levels - 1, :, engine.d:].to(device), means)
+    last = outh[levels - 1]
+    got_s, got_m = (last[:, :engine.d], last[:, engine.d:]) if engine.R == 1 else (last[0], last[1])
+    same = torch.equal(got_s.to(device), sums) and torch.equal(got_m.to(device), means)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()

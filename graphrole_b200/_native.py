@@ -317,15 +317,16 @@ class CsrHandle:
     def levels_host_sharded(self, X_host, col0, d, levels, row_offset, replicas_even,
                             replicas_odd, flag_ptrs, rank, epoch, out_host, stream=None):
         """gr_refex_levels_host_sharded_f32.  X_host: pinned float32 [n_cols, >= col0 + d];
-        out_host: [levels, n_rows, 2*d].  Returns the advanced barrier epoch."""
+        out_host: [levels, 2, n_rows, d] (sum rows, then mean rows).  Returns the advanced barrier
+        epoch."""
         import torch
         if X_host.dtype != torch.float32 or X_host.is_cuda or X_host.dim() != 2 \
                 or X_host.shape[0] != self.n_cols or X_host.stride(1) != 1 \
                 or X_host.shape[1] < col0 + d:
             raise ValueError('X_host must be a float32 CPU [n_cols, >= col0 + d] tensor')
-        if tuple(out_host.shape) != (levels, self.n_rows, 2 * d) or not out_host.is_contiguous() \
+        if tuple(out_host.shape) != (levels, 2, self.n_rows, d) or not out_host.is_contiguous() \
                 or out_host.dtype != torch.float32:
-            raise ValueError('out_host must be contiguous float32 [levels, n_rows, 2*d]')
+            raise ValueError('out_host must be contiguous float32 [levels, 2, n_rows, d]')
         k = len(replicas_even)
         ev = (c_void_p * k)(*[c_void_p(int(p)) for p in replicas_even])
         od = (c_void_p * k)(*[c_void_p(int(p)) for p in replicas_odd])

@@ -188,7 +188,7 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
                  const float* __restrict__ W, const float* __restrict__ H, int r,
                  int64_t rows_per_split, double* __restrict__ out) {
     constexpr int RB = 32;
-    __shared__ float Ws[RB][RP];
+    __shared__ __align__(16) float Ws[RB][RP];
     __shared__ double red[kThreads / 32];
     const int col = blockIdx.x * kThreads + threadIdx.x;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
@@ -205,14 +205,34 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
         }
         __syncthreads();
         if (col < f) {
-            const int cnt = (int)min((int64_t)RB, r_hi - b);
+            // four rows at a time: their X loads are independent (four requests in flight per
+            // thread instead of one) and W comes out of shared memory as float4 broadcasts --
+            // one LDS.128 per four FMAs instead of one LDS per FMA.  Rows past r_hi have W = 0
+            // and X read as 0, so they add nothing; the fp32 partial keeps the row order.
             float part = 0.f;
-            for (int a = 0; a < cnt; ++a) {
-                float wh = 0.f;
+#pragma unroll 2
+            for (int a = 0; a < RB; a += 4) {
+                float x[4], wh[4];
 #pragma unroll
-                for (int l = 0; l < RP; ++l) wh = fmaf(Ws[a][l], h[l], wh);
-                const float diff = __ldg(X + (b + a) * ldx + col) - wh;
-                part = fmaf(diff, diff, part);
+                for (int u = 0; u < 4; ++u) {
+                    x[u] = b + a + u < r_hi ? __ldg(X + (b + a + u) * ldx + col) : 0.f;
+                    wh[u] = 0.f;
+                }
+#pragma unroll
+                for (int l4 = 0; l4 < RP / 4; ++l4)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 w = *reinterpret_cast<const float4*>(&Ws[a + u][4 * l4]);
+                        wh[u] = fmaf(w.x, h[4 * l4], wh[u]);
+                        wh[u] = fmaf(w.y, h[4 * l4 + 1], wh[u]);
+                        wh[u] = fmaf(w.z, h[4 * l4 + 2], wh[u]);
+                        wh[u] = fmaf(w.w, h[4 * l4 + 3], wh[u]);
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float diff = x[u] - wh[u];
+                    part = fmaf(diff, diff, part);
+                }
             }
             total += (double)part;
         }

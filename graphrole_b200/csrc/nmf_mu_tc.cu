@@ -69,7 +69,6 @@ using namespace gr;
 namespace {
 
 constexpr int kThreads = 224;
-constexpr int kThreadsSend = 352;   // CTA pairs: + 4 sender warps (TMEM lane quarters 3, 0, 1, 2)
 constexpr int kBlockRows = 64;      // rows of X per block (UMMA M of P1)
 constexpr int kRP = 32;             // roles padded (UMMA N)
 constexpr int kBoxCols = 32;        // 32 fp32 = 128 B = one swizzle row
@@ -110,7 +109,6 @@ struct TcParams {
     float* part_wtw;     // [grid, 32, r]
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
     int cluster;         // CTAs per row block (1 or 2); must match the launch's cluster size
-    int send;            // CL = 2: dedicated sender warps for the partial X H^T exchange (352 threads)
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
                          // 8 skip P2 TMA loads + MMAs (results are then meaningless: timing only)
 };
@@ -172,12 +170,6 @@ __device__ __forceinline__ void st_async_v2(uint32_t addr, float a, float b, uin
     asm volatile(
         "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
         ::"r"(addr), "f"(a), "f"(b), "r"(remote_bar) : "memory");
-}
-// arrive on a barrier of another CTA of the cluster (address from mapa); release at cluster scope
-// orders this thread's earlier shared-memory reads before the arrive
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar)
-                 : "memory");
 }
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -337,10 +329,10 @@ __host__ __device__ inline SmemLayout smem_layout(int groups, int ring_a, int ri
 // barrier slots
 enum { B_FULL_A = 0, B_EMPTY_A = 8, B_FULL_B = 16, B_EMPTY_B = 20, B_HFULL = 24, B_D1FULL = 25,
        B_D1EMPTY = 28, B_WFULL = 31, B_WEMPTY = 32, B_D2FULL = 33, B_WINFULL = 34, B_XCHFULL = 37,
-       B_XCHFREE = 40, B_COUNT = 43 };
+       B_COUNT = 40 };
 
 template <int CL>
-__global__ void __launch_bounds__(kThreadsSend, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     const __grid_constant__ CUtensorMap map_x_mn,
                     const __grid_constant__ CUtensorMap map_h,
@@ -368,13 +360,6 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NA = p.ring_a, NB = p.ring_b;
-    // Dedicated sender warps (CTA pairs only).  Without them one warp group does both halves of
-    // the exchange: it can only start the W update of block i after it has waited for D1FULL(i+1)
-    // and sent that partial, so WFULL(i) -- and with it the W tile load of block i + 2 -- trails
-    // D1FULL(i+1) by ~1.5 us and the MMA thread spins ~15 % of its time on WINFULL
-    // (profiles/r1_ncu_nmf_tc_s3_stalls.txt).  With senders the update of block i starts as soon
-    // as the peer's partial has crossed the cluster.
-    const bool SEND = CL > 1 && p.send != 0;
     // D1 / Den buffers and how many blocks P2 trails P1 in the MMA issue order.  With CTA pairs
     // the epilogue is software-pipelined (the peer's partial needs ~1.5 us to cross the cluster),
     // so block i's updated W exists one block later than with a single CTA.
@@ -392,13 +377,9 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         mbar_init(bar(B_HFULL), 1);
         for (int i = 0; i < 3; ++i) {
             mbar_init(bar(B_D1FULL + i), 1);
-            // every warp that reads the D1 / Den buffers releases it: the 4 epilogue warps (+ the 4
-            // sender warps)
-            mbar_init(bar(B_D1EMPTY + i), SEND ? 8 : 4);
+            mbar_init(bar(B_D1EMPTY + i), 4);
             // CL = 2: one arrive.expect_tx per local epilogue warp + the peer's st.async bytes
             mbar_init(bar(B_XCHFULL + i), 4);
-            // SEND: the peer's 4 epilogue warps report that they have read exchange buffer i
-            mbar_init(bar(B_XCHFREE + i), 4);
         }
         mbar_init(bar(B_WFULL), 4);
         mbar_init(bar(B_WEMPTY), 1);
@@ -560,38 +541,6 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             }
             tc_commit(bar(B_D2FULL));
         }
-    } else if (warp >= 7) {
-        // ================= sender warps (CL = 2, SEND): own partial X H^T -> the peer ============
-        if constexpr (CL > 1) {
-            const int q = warp & 3;
-            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            const int ra = q * 16 + (lane >> 2), cp = 2 * (lane & 3);
-            auto off_f32 = [](int k, int c) {
-                return (uint32_t)k * 128u + (uint32_t)((((c >> 2) ^ (k & 7)) << 4) | ((c & 3) << 2));
-            };
-            const uint32_t peer = (uint32_t)(rank ^ 1);
-            for (int64_t jj = 0; jj < nb; ++jj) {
-                const int b = (int)(jj % 3);
-                // flow control: the peer has read block jj - 3 out of its exchange buffer b
-                if (jj >= 3)
-                    mbar_wait_acquire_cluster(bar(B_XCHFREE + b), (uint32_t)(((jj / 3) - 1) & 1));
-                mbar_wait(bar(B_D1FULL + b), (uint32_t)((jj / 3) & 1));
-                tc_fence_after();
-                float part[16];
-                tc_ld_16x32(tmem + lane_base + kColD1 + b * kRP, part);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(B_D1EMPTY + b));
-                const uint32_t dst = mapa(s_xch + b * kWnewBytes, peer);
-                const uint32_t rbar = mapa(bar(B_XCHFULL + b), peer);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        st_async_v2(dst + off_f32(ra + 8 * h, 8 * j + cp), part[4 * j + 2 * h],
-                                    part[4 * j + 2 * h + 1], rbar);
-            }
-        }
     } else {
         // ================= epilogue warps (TMEM lane quarter q) =================
         const int q = warp & 3;
@@ -730,10 +679,8 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                         }
                     __syncwarp();
                     if (lane == 0 && i + 3 < nb) mbar_expect_tx(bar(B_XCHFULL + b), kWSubBytes);
-                    // tell the peer's sender that this exchange buffer may be overwritten
-                    if (SEND && lane == 0) mbar_arrive_remote(mapa(bar(B_XCHFREE + b), peer));
                 }
-                if (jj < nb && !SEND) {
+                if (jj < nb) {
                     const int b = (int)(jj % 3);
                     mbar_wait(bar(B_D1FULL + b), (uint32_t)((jj / 3) & 1));
                     tc_fence_after();
@@ -752,10 +699,6 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                 }
                 if (i >= 0) {
                     const int b = (int)(i % 3), wb = b;
-                    if (SEND) {     // nobody in this warp has waited for block i's accumulators yet
-                        mbar_wait(bar(B_D1FULL + b), (uint32_t)((i / 3) & 1));
-                        tc_fence_after();
-                    }
                     mbar_wait(bar(B_WINFULL + wb), (uint32_t)((i / 3) & 1));    // W tile of block i
                     float xht[16], den[16], wn[16];
                     tc_ld_16x32(tmem + lane_base + kColD1 + b * kRP, xht);
@@ -1002,11 +945,9 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     }
     p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
     p.cluster = s->cluster;
-    // dedicated sender warps for the CTA-pair exchange (GR_NMF_NO_SENDERS=1: the single warp group)
-    p.send = s->cluster == 2 && !getenv("GR_NMF_NO_SENDERS");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)s->grid);
-    cfg.blockDim = dim3(p.send ? kThreadsSend : kThreads);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = s->smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

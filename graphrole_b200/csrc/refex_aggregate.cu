@@ -34,6 +34,10 @@ constexpr int kWarps = 8;      // 256 threads per CTA
 constexpr int kMinBlocks = 8;  // 32 registers/thread -> 64 resident warps per SM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxReplicas = 16;
+// Gathers per lane in flight for rows of 64 / 128 bytes (LPR = 4 / 8).  Measured on C3
+// (profiles/r2_narrow_u.txt): d = 32 all rows 10.39 -> 9.62 ms, a hub-heavy quarter 4.50 -> 3.06,
+// a tail quarter 2.88 -> 2.75; d = 16 7.74 -> 7.55; 32-byte rows (LPR = 2) do not gain.
+constexpr int kNarrowRowGathers = 2;
 
 struct RefexArgs {
     const int64_t* __restrict__ rowptr;
@@ -179,7 +183,7 @@ struct ArcStream {
 // Sum of X[colidx[k], col..col+VW) over span offsets k in [beg, end); result replicated in
 // every lane group.  One gather per lane in flight; 32/LPR lane groups -> that many
 // independent fp32 accumulators per column.
-template <int LPR, int VW>
+template <int LPR, int VW, int U>
 __device__ __forceinline__ void reduce_arcs(ArcStream& s, uint32_t beg, uint32_t end,
                                             const float* __restrict__ xcol, int64_t ldx,
                                             bool col_ok, int lane, uint64_t pol_hot,
@@ -195,15 +199,35 @@ __device__ __forceinline__ void reduce_arcs(ArcStream& s, uint32_t beg, uint32_t
         s.seek(k, lane);
         const int off = (int)(k - s.base);
         const int cnt = (int)min(end - k, (uint32_t)(32 - off));
+        if constexpr (U == 1) {
 #pragma unroll 4
-        for (int t = 0; t < cnt; t += G) {   // warp-uniform trip count (shuffles inside)
-            const int kk = t + grp;
-            const int32_t tagged = __shfl_sync(kFull, s.cur, (off + kk) & 31);
-            float v[VW];
-            load_row<VW>(v, xcol + (int64_t)(tagged & 0x7fffffff) * ldx, col_ok && kk < cnt,
-                         tagged < 0, pol_hot);
+            for (int t = 0; t < cnt; t += G) {   // warp-uniform trip count (shuffles inside)
+                const int kk = t + grp;
+                const int32_t tagged = __shfl_sync(kFull, s.cur, (off + kk) & 31);
+                float v[VW];
+                load_row<VW>(v, xcol + (int64_t)(tagged & 0x7fffffff) * ldx, col_ok && kk < cnt,
+                             tagged < 0, pol_hot);
 #pragma unroll
-            for (int c = 0; c < VW; ++c) acc[c] += v[c];
+                for (int c = 0; c < VW; ++c) acc[c] += v[c];
+            }
+        } else {
+            // two gathers per lane in flight (narrow rows: the same bytes in flight per SM as a
+            // 256-byte row with one); the additions keep the order of the U == 1 loop
+#pragma unroll 2
+            for (int t = 0; t < cnt; t += 2 * G) {
+                const int k0 = t + grp, k1 = t + G + grp;
+                const int32_t tag0 = __shfl_sync(kFull, s.cur, (off + k0) & 31);
+                const int32_t tag1 = __shfl_sync(kFull, s.cur, (off + k1) & 31);
+                float v0[VW], v1[VW];
+                load_row<VW>(v0, xcol + (int64_t)(tag0 & 0x7fffffff) * ldx, col_ok && k0 < cnt,
+                             tag0 < 0, pol_hot);
+                load_row<VW>(v1, xcol + (int64_t)(tag1 & 0x7fffffff) * ldx, col_ok && k1 < cnt,
+                             tag1 < 0, pol_hot);
+#pragma unroll
+                for (int c = 0; c < VW; ++c) acc[c] += v0[c];
+#pragma unroll
+                for (int c = 0; c < VW; ++c) acc[c] += v1[c];
+            }
         }
         k += cnt;
     }
@@ -220,7 +244,7 @@ __device__ __forceinline__ void reduce_arcs(ArcStream& s, uint32_t beg, uint32_t
 // CTAs [0, n_seg_blocks): one warp per hub segment (kHubSegment arcs of a long row -> fp32
 // partial); they lead the grid so the long warps start first and overlap the ordinary rows.
 // Remaining CTAs: rows_per_warp consecutive ordinary rows per warp.
-template <int LPR, int VW, bool BCAST>
+template <int LPR, int VW, bool BCAST, int U>
 __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* rep) {
     constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -241,7 +265,7 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
         s.limit = (uint32_t)(end - base);
         s.open((uint32_t)(beg - base), lane);
         float tot[VW];
-        reduce_arcs<LPR, VW>(s, (uint32_t)(beg - base), s.limit, xcol, a.ldx, col_ok, lane,
+        reduce_arcs<LPR, VW, U>(s, (uint32_t)(beg - base), s.limit, xcol, a.ldx, col_ok, lane,
                              pol_hot, tot);
         if (col_ok && grp == 0) store_sum<VW>(a.partial + seg * a.d + col, tot);
         return;
@@ -267,7 +291,7 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
         const uint32_t deg = end - beg;
         if (deg > a.hub_threshold) continue;  // segment warps + hub_fixup_kernel
         float tot[VW];
-        reduce_arcs<LPR, VW>(s, beg, end, xcol, a.ldx, col_ok, lane, pol_hot, tot);
+        reduce_arcs<LPR, VW, U>(s, beg, end, xcol, a.ldx, col_ok, lane, pol_hot, tot);
         if (!col_ok) continue;
         const int64_t o = (first + r) * a.ldo + col;
         // lane group 0 writes the sum block, group 1 (or the same lanes when LPR == 32) the mean
@@ -287,14 +311,28 @@ __device__ __forceinline__ void gather_body(const RefexArgs& a, const Replicas* 
 template <int LPR, int VW>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 refex_gather_kernel(const RefexArgs a) {
-    gather_body<LPR, VW, false>(a, nullptr);
+    gather_body<LPR, VW, false, 1>(a, nullptr);
 }
 
 // Same gather, mean rows broadcast to every replica (own + peers over NVLink).
 template <int LPR, int VW>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 refex_gather_bcast_kernel(const RefexArgs a, const Replicas rep) {
-    gather_body<LPR, VW, true>(a, &rep);
+    gather_body<LPR, VW, true, 1>(a, &rep);
+}
+
+// Narrow rows (at most 32 fp32 columns, e.g. a column-group shard): two gathers per lane in
+// flight, 40 registers, 48 resident warps per SM.
+constexpr int kMinBlocksU2 = 6;
+template <int LPR, int VW>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocksU2)
+refex_gather_u2_kernel(const RefexArgs a) {
+    gather_body<LPR, VW, false, 2>(a, nullptr);
+}
+template <int LPR, int VW>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocksU2)
+refex_gather_bcast_u2_kernel(const RefexArgs a, const Replicas rep) {
+    gather_body<LPR, VW, true, 2>(a, &rep);
 }
 
 // One warp per hub row: add the row's segment partials in fp64, in segment order.
@@ -321,10 +359,26 @@ hub_fixup_kernel(const int64_t* __restrict__ hub_row, const int64_t* __restrict_
 }
 
 // ---- launch plumbing --------------------------------------------------------------------
+int env_int(const char* name, int dflt, int lo, int hi);
+
 template <int LPR, int VW>
 cudaError_t launch_gather(const RefexArgs& a, const Replicas* rep, dim3 row_grid, dim3 seg_grid,
                           cudaStream_t st) {
     dim3 grid(row_grid.x + seg_grid.x, row_grid.y, 1);
+    // rows of at most 128 bytes: two gathers per lane (GR_REFEX_U=1 / 2 overrides)
+    bool u2 = false;
+    if constexpr (VW == 4 && (LPR == 4 || LPR == 8))
+        u2 = env_int("GR_REFEX_U", kNarrowRowGathers, 1, 2) == 2;
+    if constexpr (VW == 4 && (LPR == 4 || LPR == 8)) {
+        if (u2) {
+            if (rep)
+                refex_gather_bcast_u2_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a, *rep);
+            else
+                refex_gather_u2_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a);
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     if (rep)
         refex_gather_bcast_kernel<LPR, VW><<<grid, kWarps * 32, 0, st>>>(a, *rep);
     else
@@ -610,7 +664,6 @@ extern "C" int gr_refex_levels_host_sharded_f32(
         *epoch_inout += 1;
         if (int rc = gr_peer_barrier(flag_arrays, n_ranks, rank, *epoch_inout, 0.0, st)) return rc;
     }
-    const size_t out_pitch = 2 * row_bytes;
     const size_t level_floats = (size_t)g->n_rows * 2 * (size_t)d;
     for (int l = 0; l < levels; ++l) {
         const int slot = l & 1;
@@ -634,14 +687,15 @@ extern "C" int gr_refex_levels_host_sharded_f32(
         }
         if (g->n_rows > 0) {
             GR_CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->ev_level[slot], 0));
+            // two contiguous copies (a pitched copy of 128-byte rows runs at a fraction of the
+            // PCIe rate): the level's sum rows, then its mean rows
             float* dst = out_host + (size_t)l * level_floats;
-            GR_CUDA_TRY(cudaMemcpy2DAsync(dst, out_pitch, sums, row_bytes, row_bytes,
-                                          (size_t)g->n_rows, cudaMemcpyDeviceToHost,
-                                          g->copy_stream));
-            GR_CUDA_TRY(cudaMemcpy2DAsync(dst + d, out_pitch,
-                                          outs[rank] + (size_t)row_offset * d, row_bytes,
-                                          row_bytes, (size_t)g->n_rows, cudaMemcpyDeviceToHost,
-                                          g->copy_stream));
+            const size_t block_bytes = (size_t)g->n_rows * row_bytes;
+            GR_CUDA_TRY(cudaMemcpyAsync(dst, sums, block_bytes, cudaMemcpyDeviceToHost,
+                                        g->copy_stream));
+            GR_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)g->n_rows * d,
+                                        outs[rank] + (size_t)row_offset * d, block_bytes,
+                                        cudaMemcpyDeviceToHost, g->copy_stream));
         }
         GR_CUDA_TRY(cudaEventRecord(g->ev_copied[slot], g->copy_stream));
     }

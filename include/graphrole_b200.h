@@ -165,7 +165,9 @@ int gr_refex_levels_host_f32(gr_csr_t* g, const float* X_host, int64_t ldx, int3
  * PCIe and pushes them to the peers' replicas over NVLink (the ranks' row ranges must tile
  * [0, n_cols)).  Each level is gr_refex_aggregate_bcast_f32 into
  * the other replica set followed by gr_peer_barrier; the OWN rows of every level are copied
- * back, overlapped with the next level: out_host [levels, n_rows, 2*d] (sum block | mean block).
+ * back, overlapped with the next level: out_host [levels][2][n_rows][d] -- per level the sum
+ * rows then the mean rows, each one contiguous block (the agg-major order of
+ * extract.py:158-162 at block level; pitched copies of narrow rows waste the PCIe link).
  *   replicas_even / replicas_odd  n_ranks device pointers each: base of every rank's [n_cols, d]
  *                  replica used as input of the even / odd levels (own at index `rank`)
  *   flag_arrays, epoch_inout      as gr_peer_barrier; *epoch_inout is advanced levels + 1 times

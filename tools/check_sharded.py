@@ -96,7 +96,9 @@ def main():
         if eng.exchange in ('peer', 'none'):
             Xh = torch.empty((g.n, d), dtype=torch.float32, pin_memory=True)
             Xh.copy_(X0)
-            outh = torch.empty((args.levels, hi - lo, 2 * dl), dtype=torch.float32,
+            sharded = eng.R > 1
+            outh = torch.empty((args.levels, 2, hi - lo, dl) if sharded else
+                               (args.levels, hi - lo, 2 * dl), dtype=torch.float32,
                                pin_memory=True)
             for _ in range(2):                          # twice: buffers and epochs are reused
                 outh.fill_(-1.0)
@@ -104,7 +106,10 @@ def main():
                 dist.barrier()
                 for level in range(args.levels):
                     ref = ref_levels[level]
-                    if not torch.equal(outh[level].to(device), ref[lo:hi]):
+                    got = outh[level].to(device)
+                    if sharded:
+                        got = torch.cat([got[0], got[1]], dim=1)
+                    if not torch.equal(got, ref[lo:hi]):
                         failures += 1
                         print(f'[rank {rank}] MISMATCH host path mode={mode} C={C} '
                               f'level={level}', flush=True)
