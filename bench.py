@@ -335,6 +335,8 @@ def run_gpu_arm(args):
                              '(one rank per GPU)')
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    # pinned staging buffers of the e2e path should live on the GPU's own NUMA node
+    numa_note = shard_mod.bind_host_thread_to_gpu(local_rank) if world > 1 else 'single process'
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -455,6 +457,7 @@ def run_gpu_arm(args):
     if not args.no_e2e:
         try:
             line['e2e'] = e2e_section(engine, X0, n, nnz, d, levels, dist, device, args)
+            line['e2e']['host_numa'] = numa_note
         except Exception as exc:
             line['e2e'] = {'error': repr(exc)}
     engine.close()

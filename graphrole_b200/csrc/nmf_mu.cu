@@ -205,23 +205,23 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
         }
         __syncthreads();
         if (col < f) {
-            // four rows at a time: their X loads are independent (four requests in flight per
-            // thread instead of one) and W comes out of shared memory as float4 broadcasts --
-            // one LDS.128 per four FMAs instead of one LDS per FMA.  Rows past r_hi have W = 0
+            // sixteen rows at a time: their X loads are independent (16 requests in flight per
+            // thread -- with one, the pass ran at 1.9 TB/s on C5 -- ) and W comes out of shared
+            // memory as float4 broadcasts: one LDS.128 per four FMAs.  Rows past r_hi have W = 0
             // and X read as 0, so they add nothing; the fp32 partial keeps the row order.
+            constexpr int UR = 16;
             float part = 0.f;
-#pragma unroll 2
-            for (int a = 0; a < RB; a += 4) {
-                float x[4], wh[4];
+            for (int a = 0; a < RB; a += UR) {
+                float x[UR], wh[UR];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UR; ++u) {
                     x[u] = b + a + u < r_hi ? __ldg(X + (b + a + u) * ldx + col) : 0.f;
                     wh[u] = 0.f;
                 }
 #pragma unroll
                 for (int l4 = 0; l4 < RP / 4; ++l4)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < UR; ++u) {
                         const float4 w = *reinterpret_cast<const float4*>(&Ws[a + u][4 * l4]);
                         wh[u] = fmaf(w.x, h[4 * l4], wh[u]);
                         wh[u] = fmaf(w.y, h[4 * l4 + 1], wh[u]);
@@ -229,7 +229,7 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
                         wh[u] = fmaf(w.w, h[4 * l4 + 3], wh[u]);
                     }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UR; ++u) {
                     const float diff = x[u] - wh[u];
                     part = fmaf(diff, diff, part);
                 }
@@ -243,6 +243,86 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+        out[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+// ---- ||X - W H||_F^2, register-tiled: CTA = 128 columns, 128-row steps, 8 x 8 outputs per thread --
+// The thread-per-column kernel above spends one shared-memory load per four FMAs and keeps one
+// row in flight per step: on C5 it ran at 10 ms (r = 4) - 22 ms (r = 32) per pass.  Here every
+// thread holds an 8 x 8 block of W.H in registers (10 shared-memory loads per 64 FMAs), its 16
+// float4 loads of X are issued before the FMAs, and the pass is bound by the X stream (small r)
+// or by FFMA issue (r = 32).  Needs f % 4 == 0 and 16-byte aligned rows; the kernel above stays
+// as the general form.  Rows past r_hi and columns past f contribute exactly 0.
+constexpr int kErrTile = 128;
+constexpr int kMaxErrParts = 8192;
+template <int RP>
+__global__ void __launch_bounds__(256, 1)
+nmf_error_tile_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
+                      const float* __restrict__ W, const float* __restrict__ H, int r,
+                      int64_t rows_per_split, double* __restrict__ out) {
+    __shared__ __align__(16) float Hs[RP][kErrTile];
+    __shared__ float Ws[kErrTile][RP + 1];   // +1: the two row groups of a warp hit different banks
+    __shared__ double red[8];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int col0 = (int)blockIdx.x * kErrTile, c = col0 + tx * 8;
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_hi = min(n, r_lo + rows_per_split);
+    for (int i = threadIdx.x; i < RP * kErrTile; i += 256) {
+        const int k = i / kErrTile, cc = i % kErrTile;
+        Hs[k][cc] = (k < r && col0 + cc < f) ? __ldg(H + (int64_t)k * f + col0 + cc) : 0.f;
+    }
+    double total = 0.0;
+    for (int64_t b = r_lo; b < r_hi; b += kErrTile) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kErrTile * RP; i += 256) {
+            const int row = i / RP, k = i % RP;
+            Ws[row][k] = (b + row < r_hi && k < r) ? __ldg(W + (b + row) * r + k) : 0.f;
+        }
+        __syncthreads();
+        float x[8][8], acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t row = b + ty * 8 + i;
+            const bool row_ok = row < r_hi;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_ok && c + 4 * v < f)
+                    t = __ldcs(reinterpret_cast<const float4*>(X + row * ldx + c + 4 * v));
+                x[i][4 * v] = t.x; x[i][4 * v + 1] = t.y; x[i][4 * v + 2] = t.z; x[i][4 * v + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        }
+#pragma unroll 4
+        for (int k = 0; k < RP; ++k) {
+            const float4 h0 = *reinterpret_cast<const float4*>(&Hs[k][tx * 8]);
+            const float4 h1 = *reinterpret_cast<const float4*>(&Hs[k][tx * 8 + 4]);
+            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float w = Ws[ty * 8 + i][k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w, hv[j], acc[i][j]);
+            }
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float diff = x[i][j] - acc[i][j];
+                part = fmaf(diff, diff, part);
+            }
+        total += (double)part;
+    }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
         out[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
 }
@@ -313,8 +393,29 @@ int gr::nmf_finish_iteration(gr_nmf* h, const float* part_wtx, const float* part
 
 int gr::nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const float* H,
                   double* err, cudaStream_t st) {
-    const int slabs = ceil_div(h->f, kThreads);
-    if (int rc = dispatch_rp(h->rp, [&](auto RPc) {
+    int slabs = ceil_div(h->f, kThreads);
+    int splits = h->splits;
+    const bool tiled = h->f % 4 == 0 && ldx % 4 == 0 && aligned16(X) && !getenv("GR_NMF_ERROR_SIMPLE");
+    if (tiled) {
+        // 128-column blocks x row splits of whole 128-row steps: about two CTAs per SM in total
+        slabs = ceil_div(h->f, kErrTile);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const int64_t steps = ceil_div<int64_t>(h->n, kErrTile);
+        int64_t want = std::max<int64_t>(1, std::min<int64_t>(steps, (2 * sms + slabs - 1) / slabs));
+        want = std::min<int64_t>(want, kMaxErrParts / slabs);
+        const int64_t rows_per_split = ceil_div<int64_t>(steps, want) * kErrTile;
+        splits = (int)ceil_div<int64_t>(h->n, rows_per_split);
+        if (int rc = dispatch_rp(h->rp, [&](auto RPc) {
+                constexpr int RP = decltype(RPc)::value;
+                dim3 g((unsigned)slabs, (unsigned)splits);
+                nmf_error_tile_kernel<RP><<<g, 256, 0, st>>>(X, ldx, h->n, h->f, W, H, h->r,
+                                                             rows_per_split, h->d_err_part);
+                GR_LAUNCH_CHECK("nmf_error_tile_kernel");
+                return (int)GR_OK;
+            }))
+            return rc;
+    } else if (int rc = dispatch_rp(h->rp, [&](auto RPc) {
             constexpr int RP = decltype(RPc)::value;
             dim3 g((unsigned)slabs, (unsigned)h->splits);
             nmf_error_kernel<RP><<<g, kThreads, 0, st>>>(X, ldx, h->n, h->f, W, H, h->r,
@@ -323,7 +424,7 @@ int gr::nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const 
             return (int)GR_OK;
         }))
         return rc;
-    const size_t cnt = (size_t)slabs * h->splits;
+    const size_t cnt = (size_t)slabs * splits;
     h->h_err_part.resize(cnt);
     GR_CUDA_TRY(cudaMemcpyAsync(h->h_err_part.data(), h->d_err_part, cnt * sizeof(double),
                                 cudaMemcpyDeviceToHost, st));
@@ -365,7 +466,7 @@ extern "C" int gr_nmf_create(gr_nmf_t** out, int64_t n, int32_t f, int32_t r, in
                     alloc(&h->d_h_next, (size_t)r * f) &&
                     alloc(&h->d_part_wtx, (size_t)h->splits * h->rp * f) &&
                     alloc(&h->d_part_wtw, (size_t)h->splits * h->rp * r) &&
-                    alloc(&h->d_err_part, (size_t)slabs * h->splits);
+                    alloc(&h->d_err_part, std::max<size_t>((size_t)slabs * h->splits, kMaxErrParts));
     if (!ok) {
         cudaGetLastError();
         gr_nmf_destroy(h);

@@ -582,8 +582,15 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     const float2 w = *wp;
                     const float d0 = den[e] == 0.f ? kEps : den[e];
                     const float d1 = den[e + 1] == 0.f ? kEps : den[e + 1];
-                    wn[e] = c < r ? w.x * __fdividef(xht[e], d0) : 0.f;
-                    wn[e + 1] = c + 1 < r ? w.y * __fdividef(xht[e + 1], d1) : 0.f;
+                    // The updated W is rounded to tf32 (nearest) BEFORE it is stored: next
+                    // iteration's W (H H^T) MMA reads this tile as raw fp32 bits, i.e. truncated to
+                    // tf32, and a truncated operand is low by ~3.4e-4 on average -- the denominator
+                    // was biased, W grew and H shrank by that factor every iteration (measured
+                    // against sklearn from a shared start: both factors off by 1.8e-2 after 50
+                    // iterations with the reconstruction equal to 1e-6).  With W held at tf32
+                    // precision the truncation is exact and every operand rounding is unbiased.
+                    wn[e] = c < r ? to_tf32(w.x * __fdividef(xht[e], d0)) : 0.f;
+                    wn[e + 1] = c + 1 < r ? to_tf32(w.y * __fdividef(xht[e + 1], d1)) : 0.f;
                     *wp = make_float2(wn[e], wn[e + 1]);
                 }
         };

@@ -164,14 +164,12 @@ class DeviceRecursiveFeatureExtractor:
         if redundant:
             with self._timed('compact'):
                 keep = [k for k, name in enumerate(all_names) if name not in redundant]
-                # rows only move towards the front: gather the kept rows behind the first removed
-                # one through a temporary (index_select never aliases its output)
                 first = next(k for k, name in enumerate(all_names) if name in redundant)
                 tail = [k for k in keep if k > first]
-                if tail:
-                    moved = self._bins_buf.index_select(
-                        0, torch.tensor(tail, device=self.device))
-                    self._bins_buf[first:first + len(tail)].copy_(moved)
+                # kept rows move one by one towards the front (row k lands at or before k, in
+                # ascending order, so nothing is overwritten before it has been read)
+                for dst, src in enumerate(tail, start=first):
+                    self._bins_buf[dst].copy_(self._bins_buf[src])
             for name in redundant:
                 self._names.remove(name)
                 del self._columns[name]

@@ -30,6 +30,32 @@ import torch
 from graphrole_b200.graph.csr import CSRGraph
 
 
+def bind_host_thread_to_gpu(device_index: int) -> str:
+    """Pin the calling thread to the CPU cores next to GPU `device_index` (NVML's ideal CPU
+    affinity), so that the pinned host buffers it allocates afterwards land on that GPU's NUMA
+    node.  One process per GPU all first-touching their staging buffers on the same node is what
+    limits the host-buffer path on an 8-GPU box: measured 14.5 GB/s of D2H per GPU at 8 ranks
+    against 50 GB/s for one.  Returns a note for the bench line; never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        handle = None
+        uuid = getattr(props, 'uuid', None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(f'GPU-{uuid}'.encode())
+            except Exception:
+                handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f'host thread bound to {len(cpus)} CPUs next to the GPU ({cpus[0]}..{cpus[-1]})'
+    except Exception as exc:          # no NVML, no permission, a container without cpusets ...
+        return f'host thread not bound ({exc!r})'
+
+
 def nnz_balanced_ranges(rowptr: torch.Tensor, world: int) -> List[Tuple[int, int]]:
     """Contiguous row ranges with (nearly) equal arc counts; every row belongs to one range."""
     n = rowptr.numel() - 1

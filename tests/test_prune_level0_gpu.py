@@ -293,6 +293,40 @@ def test_level0_device_hub_rows_and_frames():
     assert np.array_equal(frame['internal_edges'].values, (d + tri).astype(np.int64))
 
 
+def test_level0_triangle_fast_path_equals_general_kernels(refex_cases, monkeypatch):
+    """Undirected + unweighted + no self loop graphs take the triangle-counting path on the
+    degree-oriented graph (csrc/level0.cu); it must give exactly what the general
+    sorted-intersection kernels give (GR_LEVEL0_GENERAL=1), on the reference's own unweighted
+    tables and on random graphs with isolated nodes, and fall back when there is a self loop."""
+    from graphrole_b200.graph.generators import erdos_renyi_csr
+    for name in ('path4', 'dangling', 'karate', 'iface_undirected'):
+        case = refex_cases[name]
+        G = graph_from_json(case['graph'])
+        labels = sorted(G.nodes)
+        row = {v: i for i, v in enumerate(labels)}
+        g = CSRGraph.from_edges([row[u] for u, _ in G.edges()], [row[v] for _, v in G.edges()],
+                                n=len(labels), labels=labels)
+        ref = frame_from_json(case['level0'])
+        cols = level0.device_features(g, DEV)
+        for col in ref.columns:
+            np.testing.assert_array_equal(cols[col].cpu().numpy(), ref[col].values, err_msg=col)
+    graphs = [erdos_renyi_csr(50_000, 400_000, seed=1, device=DEV),
+              barabasi_albert_csr(60_000, 9, seed=2, device=DEV),
+              CSRGraph.from_edges([0, 1, 5], [1, 2, 6], n=9)]        # isolated nodes 3, 4, 7, 8
+    for g in graphs:
+        fast = level0.device_features(g, DEV)
+        monkeypatch.setenv('GR_LEVEL0_GENERAL', '1')
+        general = level0.device_features(g, DEV)
+        monkeypatch.delenv('GR_LEVEL0_GENERAL')
+        for col in general:
+            assert torch.equal(fast[col], general[col]), col
+    loop = CSRGraph.from_edges([0, 1, 2, 2], [1, 2, 0, 2], n=3)          # triangle + self loop
+    got = level0.device_features(loop, DEV)
+    want = pd.concat([level0.local_degree_features(loop), level0.egonet_features(loop)], axis=1)
+    for col in got:
+        np.testing.assert_array_equal(got[col].cpu().numpy(), want[col].values.astype(float))
+
+
 # ---- device-resident recursion -------------------------------------------------------------------
 
 @pytest.mark.parametrize('name', ['dangling', 'directed_weighted', 'undirected_weighted',
