@@ -42,7 +42,7 @@ WORKLOAD_NAMES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one refex_gather_kernel launch, from the
 # `ncu --set full` capture committed under profiles/ (single GPU only; not re-measured per run)
-NCU_TRAFFIC = {'c3': {'bytes': 91.29e9 + 5.49e9, 'source': 'profiles/r1_ncu_refex_final_raw.csv'}}
+NCU_TRAFFIC = {'c3': {'bytes': 91.148e9 + 5.493e9, 'source': 'profiles/r2_ncu_refex_gather_d64_raw.csv'}}
 METRIC = 'refex_aggregated_edges_x_features_per_sec'
 UNIT = 'arc*features/s'
 RTOL = 1e-5        # north_star: feature matrices within 1e-5 relative (fp32 vs the float64 path)
@@ -630,19 +630,42 @@ def next_rows_section(g, d, device):
         return e0.elapsed_time(e1) / reps
 
     out = {}
+    peak, _ = measured_peak_hbm()
     ms = timed(lambda: level0.device_features(g))
+    # compulsory traffic of the triangle path: rowptr + colidx read by the orientation pass, the
+    # oriented copy written and read, counters: ~ (8 n + 4 nnz) * 2 + 4 nnz/2 * 2 + 24 n bytes
+    l0_bytes = (8 * g.n + 4 * g.nnz) * 2 + 4 * (g.nnz // 2) * 2 + 24 * g.n
     out['level0'] = {'ms': ms, 'arcs_per_s': g.nnz / ms * 1e3,
-                     'columns': ['degree', 'internal_edges', 'external_edges']}
+                     'columns': ['degree', 'internal_edges', 'external_edges'],
+                     'path': 'triangle counting on the degree-oriented graph (undirected, '
+                             'unweighted, no self loops)',
+                     'roofline': {'bound': 'latency of dependent binary-search loads (L2), not a '
+                                           'stream', 'compulsory_bytes': l0_bytes,
+                                  'achieved': l0_bytes / ms / 1e6, 'peak': peak, 'unit': 'GB/s',
+                                  'frac': l0_bytes / ms / 1e6 / peak}}
     feats = g.handle(device).aggregate(torch.rand(g.n, d, device=device))
     pruner = _native.Pruner(g.n, device)
     bins = torch.empty((feats.shape[1], g.n), dtype=torch.int32, device=device)
     ms = timed(lambda: pruner.bin_columns(feats, out=bins))
+    # per key: transpose pass (4 B in, 4 out), radix sort of (key, row) pairs = 4 passes x
+    # (8 B in + 8 B out), bin scatter (4 B in, 4 B out) = 80 bytes
+    bin_bytes = 80 * feats.numel()
     out['vertical_log_binning'] = {'columns': feats.shape[1], 'ms': ms,
-                                   'keys_per_s': feats.numel() / ms * 1e3}
+                                   'keys_per_s': feats.numel() / ms * 1e3,
+                                   'roofline': {'bound': 'hbm (cub radix sort passes)',
+                                                'algorithmic_bytes': bin_bytes,
+                                                'achieved': bin_bytes / ms / 1e6, 'peak': peak,
+                                                'unit': 'GB/s', 'frac': bin_bytes / ms / 1e6 / peak}}
     ms = timed(lambda: pruner.pairwise_gaps(bins), reps=2)
     f = bins.shape[0]
-    out['pairwise_gaps'] = {'columns': f, 'ms': ms,
-                            'pair_rows_per_s': f * (f - 1) / 2 * g.n / ms * 1e3}
+    # 2 fp32 ALU operations (|a - b|, max) per (pair, row); 148 SMs x 128 lanes per clock
+    pair_rows = f * (f - 1) / 2 * g.n
+    alu_peak = 148 * 128 * 1.965e9 / 2
+    out['pairwise_gaps'] = {'columns': f, 'ms': ms, 'pair_rows_per_s': pair_rows / ms * 1e3,
+                            'roofline': {'bound': 'fp32 alu (2 operations per pair and row)',
+                                         'achieved': pair_rows / ms * 1e3, 'peak': alu_peak,
+                                         'unit': 'pair*rows/s',
+                                         'frac': pair_rows / ms * 1e3 / alu_peak}}
     pruner.close()
     del feats, bins
     torch.cuda.empty_cache()

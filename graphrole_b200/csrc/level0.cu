@@ -393,6 +393,7 @@ extern "C" int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* row
     DeviceGuard guard(device);
     if (!guard.ok) return fail(GR_ERR_CUDA, "gr_level0_features_f64: cannot select device %d", device);
     if (int rc = require_sm100(device)) return rc;
+    retain_async_pool(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // undirected + unweighted (+ no self loop, checked on the device): triangle counting on the
     // degree-oriented graph; GR_LEVEL0_GENERAL=1 forces the general kernels

@@ -249,33 +249,37 @@ nmf_error_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
 
 // ---- ||X - W H||_F^2, register-tiled: CTA = 128 columns, 128-row steps, 8 x 8 outputs per thread --
 // The thread-per-column kernel above spends one shared-memory load per four FMAs and keeps one
-// row in flight per step: on C5 it ran at 10 ms (r = 4) - 22 ms (r = 32) per pass.  Here every
+// row in flight per step: on C5 it ran at 10 ms (r = 4) - 22 ms (r = 32) per pass; with 256
+// threads per CTA (one CTA per SM at 233 registers) this kernel took 8.2 - 13.6 ms.  Here every
 // thread holds an 8 x 8 block of W.H in registers (10 shared-memory loads per 64 FMAs), its 16
 // float4 loads of X are issued before the FMAs, and the pass is bound by the X stream (small r)
 // or by FFMA issue (r = 32).  Needs f % 4 == 0 and 16-byte aligned rows; the kernel above stays
 // as the general form.  Rows past r_hi and columns past f contribute exactly 0.
-constexpr int kErrTile = 128;
+constexpr int kErrTile = 128;       // columns per CTA
+constexpr int kErrRows = 64;        // rows per step: 128 threads x (8 x 8), two CTAs per SM --
+                                    // one computes while the other waits for its X loads
+constexpr int kErrThreads = 128;
 constexpr int kMaxErrParts = 8192;
 template <int RP>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kErrThreads, 2)
 nmf_error_tile_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f,
                       const float* __restrict__ W, const float* __restrict__ H, int r,
                       int64_t rows_per_split, double* __restrict__ out) {
     __shared__ __align__(16) float Hs[RP][kErrTile];
-    __shared__ float Ws[kErrTile][RP + 1];   // +1: the two row groups of a warp hit different banks
-    __shared__ double red[8];
+    __shared__ float Ws[kErrRows][RP + 1];   // +1: the two row groups of a warp hit different banks
+    __shared__ double red[kErrThreads / 32];
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     const int col0 = (int)blockIdx.x * kErrTile, c = col0 + tx * 8;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_hi = min(n, r_lo + rows_per_split);
-    for (int i = threadIdx.x; i < RP * kErrTile; i += 256) {
+    for (int i = threadIdx.x; i < RP * kErrTile; i += kErrThreads) {
         const int k = i / kErrTile, cc = i % kErrTile;
         Hs[k][cc] = (k < r && col0 + cc < f) ? __ldg(H + (int64_t)k * f + col0 + cc) : 0.f;
     }
     double total = 0.0;
-    for (int64_t b = r_lo; b < r_hi; b += kErrTile) {
+    for (int64_t b = r_lo; b < r_hi; b += kErrRows) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kErrTile * RP; i += 256) {
+        for (int i = threadIdx.x; i < kErrRows * RP; i += kErrThreads) {
             const int row = i / RP, k = i % RP;
             Ws[row][k] = (b + row < r_hi && k < r) ? __ldg(W + (b + row) * r + k) : 0.f;
         }
@@ -322,7 +326,7 @@ nmf_error_tile_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += red[w];
+        for (int w = 0; w < kErrThreads / 32; ++w) t += red[w];
         out[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
 }
@@ -401,15 +405,15 @@ int gr::nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const 
         slabs = ceil_div(h->f, kErrTile);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        const int64_t steps = ceil_div<int64_t>(h->n, kErrTile);
-        int64_t want = std::max<int64_t>(1, std::min<int64_t>(steps, (2 * sms + slabs - 1) / slabs));
+        const int64_t steps = ceil_div<int64_t>(h->n, kErrRows);
+        int64_t want = std::max<int64_t>(1, std::min<int64_t>(steps, (4 * sms + slabs - 1) / slabs));
         want = std::min<int64_t>(want, kMaxErrParts / slabs);
-        const int64_t rows_per_split = ceil_div<int64_t>(steps, want) * kErrTile;
+        const int64_t rows_per_split = ceil_div<int64_t>(steps, want) * kErrRows;
         splits = (int)ceil_div<int64_t>(h->n, rows_per_split);
         if (int rc = dispatch_rp(h->rp, [&](auto RPc) {
                 constexpr int RP = decltype(RPc)::value;
                 dim3 g((unsigned)slabs, (unsigned)splits);
-                nmf_error_tile_kernel<RP><<<g, 256, 0, st>>>(X, ldx, h->n, h->f, W, H, h->r,
+                nmf_error_tile_kernel<RP><<<g, kErrThreads, 0, st>>>(X, ldx, h->n, h->f, W, H, h->r,
                                                              rows_per_split, h->d_err_part);
                 GR_LAUNCH_CHECK("nmf_error_tile_kernel");
                 return (int)GR_OK;

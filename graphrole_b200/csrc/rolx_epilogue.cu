@@ -739,6 +739,7 @@ int kl_impl(const T* V, int64_t n, int32_t f, int64_t ldv, const T* G, int64_t l
     DeviceGuard guard(device);
     if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    retain_async_pool(device);
     const int blocks = (int)std::min<int64_t>(n, kRedBlocks * 2);
     double* partial = nullptr;
     GR_CUDA_TRY(cudaMallocAsync(&partial, (blocks + 1) * sizeof(double), st));
