@@ -600,8 +600,9 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int k = ra + 8 * h, c = 8 * j + cp, e = 4 * j + 2 * h;
+                    // wn is already rounded to tf32 by update_w
                     *reinterpret_cast<float2*>(smem + L.wnew + off_tf32(k, c)) =
-                        make_float2(to_tf32(wn[e]), to_tf32(wn[e + 1]));
+                        make_float2(wn[e], wn[e + 1]);
                 }
         };
         // W tile out (rows beyond n / roles beyond r are clipped by the tensor map), then refill a
