@@ -109,6 +109,7 @@ struct TcParams {
     float* part_wtw;     // [grid, 32, r]
     unsigned long long* trace;  // development: [4 roles][64 blocks][8 events] globaltimer ns (CTA 0)
     int cluster;         // CTAs per row block (1 or 2); must match the launch's cluster size
+    int wide_p2;         // P2 as 8 MMAs of M = 64 (roles) x N = 256 (all columns of the CTA) per block
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
                          // 8 skip P2 TMA loads + MMAs (results are then meaningless: timing only)
 };
@@ -295,6 +296,9 @@ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
 constexpr uint32_t kIdescP1 = make_idesc(64, kRP, 0, 0);    // X K-major, H K-major
 constexpr uint32_t kIdescP2 = make_idesc(kP2M, kRP, 1, 1);    // X^T MN-major, W_b MN-major
 constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 1, 1);   // W_b MN-major on both sides
+// wide P2: (W^T X)[roles, columns] = W_b^T (MN-major, M = 64: roles 32..63 alias 0..31) . X_b
+// (MN-major, N = 256 columns = both P2 stages of the block, which are adjacent in the ring)
+constexpr uint32_t kIdescP2Wide = make_idesc(64, 256, 1, 1);
 
 // ---- shared memory carve-up ---------------------------------------------------------------------
 struct SmemLayout {
@@ -505,6 +509,31 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                     mbar_wait(bar(B_WFULL), (uint32_t)(j & 1));
                     GR_TRACE(2, j, 3);
                     tc_fence_after();
+                    if (p.wide_p2) {
+                        // Both 128-column tiles of the block (ring stages 0 and 1: T == NB == 2, so
+                        // tile t always lands in stage t) as ONE B operand of 256 columns, the tf32
+                        // copy of W_b as the A operand: 8 MMAs per block instead of 16.  The tensor
+                        // pipe retires these small MMAs at a fixed ~50 - 75 cycles each, so fewer
+                        // and larger is what counts (profiles/README.md).
+                        if (!(p.debug & 8)) {
+                            mbar_wait(bar(B_FULL_B + 0), (itb / NB) & 1);
+                            mbar_wait(bar(B_FULL_B + 1), ((itb + 1) / NB) & 1);
+                        }
+                        tc_fence_after();
+                        if (!(p.debug & 10)) {
+                            const uint32_t a_lo = desc_lo(s_wnew, 0);
+                            const uint32_t b_lo = desc_lo(s_rb, kBoxBytes);
+                            constexpr uint32_t hi = desc_hi(512, kLayoutSw128Base32);
+                            const uint32_t acc0 = (uint32_t)(j != 0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                tc_mma_tf32_split(tmem + kColD2, a_lo + k * 64, hi, b_lo + k * 64,
+                                                  hi, kIdescP2Wide, acc0 | (uint32_t)k);
+                        }
+                        tc_commit(bar(B_EMPTY_B + 0));
+                        tc_commit(bar(B_EMPTY_B + 1));
+                        itb += 2;
+                    } else
                     for (int t = 0; t < T; ++t, ++itb) {
                         const int st = itb % NB;
                         if (!(p.debug & 8)) mbar_wait(bar(B_FULL_B + st), (itb / NB) & 1);
@@ -738,6 +767,21 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
         mbar_wait(bar(B_D2FULL), 0);
         tc_fence_after();
         float v[32];
+        if (p.wide_p2) {
+            // M = 64 layout: role 16q + l in lane l < 16 of quarter q (q < 2), TMEM column = the
+            // CTA's column; every thread writes 32 consecutive columns of its role
+            for (int ch = 0; ch < 8; ++ch) {
+                tc_ld_32x32(tmem + lane_base + kColD2 + ch * 32, v);
+                const int role = q * 16 + lane;
+                if (q < 2 && lane < 16 && role < r)
+#pragma unroll
+                    for (int l = 0; l < 32; ++l) {
+                        const int col = col_lo + ch * 32 + l;
+                        if (col < col_hi)
+                            p.part_wtx[((int64_t)blockIdx.x * kRP + role) * p.f + col] = v[l];
+                    }
+            }
+        } else
         for (int t = 0; t < T; ++t) {
             tc_ld_32x32(tmem + lane_base + kColD2 + t * kRP, v);
             // M=64 layout: row 16q + l in lane l < 16 of quarter q; M=128: row 32q + l in lane l
@@ -953,6 +997,10 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     }
     p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
     p.cluster = s->cluster;
+    // wide P2 needs two 128-column tiles per CTA in a two-stage ring (so that a block's tiles sit
+    // side by side in shared memory) and 256 TMEM columns behind the D1 / Den / W^T W buffers
+    p.wide_p2 = s->cluster == 2 && groups == 4 && s->ring_b == 2 && kP2M == 128 &&
+                col_d2(3) + 256 <= kTmemCols && !getenv("GR_NMF_NARROW_P2");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)s->grid);
     cfg.blockDim = dim3(kThreads);
