@@ -146,30 +146,35 @@ __global__ void pair_tile_table_kernel(int2* table, int T) {
         table[ti * T - ti * (ti - 1) / 2 + (tj - ti)] = make_int2(ti, tj);
 }
 
-// bins: column-major [d][ldb] int32.  smem chunk: [R][stride] fp32, stride = 4 * T columns
+// bins: column-major [d][ldb] int32.  smem chunk: [R][stride] fp32, stride = 4 * T4 columns
 // padded to an odd number of float4 (float4 alignment, conflict-free transposing stores).
 // grid.x = persistent chunk workers, grid.y = batches of pair tiles.  A CTA's 256 threads are
 // P pair slots x S row slices (P = power of two >= min(#pair tiles, 256)): pair tile
-// pt = blockIdx.y + slot * gridDim.y, rows slice, slice + S, ... of every chunk.
+// pt = blockIdx.y + slot * gridDim.y, rows slice, slice + S, ... of every chunk.  A thread keeps
+// the running maxima of a TS x TS block of column pairs in registers: TS = 4 (2 LDS.128 per 16
+// pairs) for narrow frames, TS = 8 (4 LDS.128 per 64 pairs: measured 25.6 -> 18.0 ms for 128
+// columns x 10 M rows, profiles/r2_exp_pairwise_tiles.txt) from 64 columns on.  T4 = number of
+// 4-column groups the chunk holds (even for TS = 8), T = number of TS-column tiles.
+template <int TS>
 __global__ void __launch_bounds__(256, 1)
-pairwise_gap_kernel(const int32_t* __restrict__ bins, int64_t ldb, int64_t n, int d, int T, int R,
+pairwise_gap_kernel(const int32_t* __restrict__ bins, int64_t ldb, int64_t n, int d, int T4, int R,
                     int P, const int2* __restrict__ pair_tiles, int n_pair_tiles,
                     int32_t* __restrict__ gap) {
     extern __shared__ float chunk[];
-    const int stride = 4 * (T + 1 + (T & 1));   // odd number of float4 per row
+    const int stride = 4 * (T4 + 1 + (T4 & 1));   // odd number of float4 per row
     const int slot = threadIdx.x % P, slice = threadIdx.x / P, S = 256 / P;
     const int pt = (int)blockIdx.y + slot * (int)gridDim.y;
     const bool active = pt < n_pair_tiles;
     const int2 t = active ? pair_tiles[pt] : make_int2(0, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float m[4][4];
+    float m[TS][TS];
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < TS; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) m[x][y] = 0.f;
+        for (int y = 0; y < TS; ++y) m[x][y] = 0.f;
 
     const int64_t n_chunks = (n + R - 1) / R;
-    const int patches_r = R / 8, n_patches = patches_r * T;
+    const int patches_r = R / 8, n_patches = patches_r * T4;
     for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const int64_t r0 = ch * R;
         __syncthreads();
@@ -183,26 +188,31 @@ pairwise_gap_kernel(const int32_t* __restrict__ bins, int64_t ldb, int64_t n, in
         }
         __syncthreads();
         if (active) {
-            const float* pa = chunk + 4 * t.x;
-            const float* pb = chunk + 4 * t.y;
-#pragma unroll 4
+            const float* pa = chunk + TS * t.x;
+            const float* pb = chunk + TS * t.y;
+#pragma unroll 2
             for (int r = slice; r < R; r += S) {
-                const float4 a = *reinterpret_cast<const float4*>(pa + r * stride);
-                const float4 b = *reinterpret_cast<const float4*>(pb + r * stride);
-                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                float av[TS], bv[TS];
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+                for (int v = 0; v < TS / 4; ++v) {
+                    const float4 a = *reinterpret_cast<const float4*>(pa + r * stride + 4 * v);
+                    const float4 b = *reinterpret_cast<const float4*>(pb + r * stride + 4 * v);
+                    av[4 * v] = a.x; av[4 * v + 1] = a.y; av[4 * v + 2] = a.z; av[4 * v + 3] = a.w;
+                    bv[4 * v] = b.x; bv[4 * v + 1] = b.y; bv[4 * v + 2] = b.z; bv[4 * v + 3] = b.w;
+                }
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) m[x][y] = fmaxf(m[x][y], fabsf(av[x] - bv[y]));
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y) m[x][y] = fmaxf(m[x][y], fabsf(av[x] - bv[y]));
             }
         }
     }
     if (active) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < TS; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int i = 4 * t.x + x, j = 4 * t.y + y;
+            for (int y = 0; y < TS; ++y) {
+                const int i = TS * t.x + x, j = TS * t.y + y;
                 if (i < d && j < d && i != j && m[x][y] > 0.f) {
                     atomicMax(&gap[i * d + j], (int)m[x][y]);
                     atomicMax(&gap[j * d + i], (int)m[x][y]);
@@ -349,38 +359,48 @@ extern "C" int gr_prune_pairwise_gap_i32(gr_pruner_t* h, const int32_t* bins_dev
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GR_CUDA_TRY(cudaMemsetAsync(gap_dev, 0, (size_t)d * d * sizeof(int32_t), st));
     if (d == 1) return GR_OK;
-    const int T = ceil_div(d, 4);
+    // 8 x 8 register tiles from 64 columns on (enough pair tiles to fill the slots), 4 x 4 below
+    const int TS = (d >= 64 && !getenv("GR_PRUNE_TILE4")) ? 8 : 4;
+    const int T = ceil_div(d, TS);
+    const int T4 = T * (TS / 4);
     const int n_pair_tiles = T * (T + 1) / 2;
-    if (h->pair_tiles_for_d != d) {
-        // the table buffer is sized once for d = 1024: re-filling it is a stream-ordered kernel,
-        // no allocation and no synchronisation per call (d changes with every generation)
+    if (h->pair_tiles_for_d != T) {
+        // the table buffer is sized once for 256 tiles per side: re-filling it is a stream-ordered
+        // kernel, no allocation and no synchronisation per call (d changes with every generation)
         if (!h->pair_tiles) {
             constexpr int kMaxT = 256;
             GR_CUDA_TRY(cudaMalloc((void**)&h->pair_tiles,
                                    (size_t)(kMaxT * (kMaxT + 1) / 2) * sizeof(int2)));
         }
-        h->pair_tiles_for_d = d;
+        h->pair_tiles_for_d = T;
         pair_tile_table_kernel<<<dim3(T, ceil_div(T, 64)), 64, 0, st>>>(h->pair_tiles, T);
         count_launch();
     }
     // rows per shared-memory chunk: as many as fit (multiple of 8, at most 256)
-    const int stride = 4 * (T + 1 + (T & 1));
+    const int stride = 4 * (T4 + 1 + (T4 & 1));
     const int budget = h->max_smem - 1024;
     int R = std::min(256, budget / (stride * 4));
     R -= R % 8;
     GR_REQUIRE(R >= 8, "gr_prune_pairwise_gap_i32: d = %d does not fit shared memory", d);
     const int64_t n_chunks = ceil_div<int64_t>(h->n, R);
     const size_t smem = (size_t)R * stride * sizeof(float);
-    GR_CUDA_TRY(cudaFuncSetAttribute(pairwise_gap_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int P = 1;
     while (P < 256 && P < n_pair_tiles) P *= 2;
     const int batches = ceil_div(n_pair_tiles, P);
     // one CTA per SM when the chunk takes most of the shared memory, more when it is small
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)budget / (smem + 1024)));
     const int workers = (int)std::min<int64_t>(n_chunks, std::max(1, per_sm * h->sms / batches));
-    pairwise_gap_kernel<<<dim3(workers, batches), 256, smem, st>>>(
-        bins_dev, ldb, h->n, d, T, R, P, h->pair_tiles, n_pair_tiles, gap_dev);
+    if (TS == 8) {
+        GR_CUDA_TRY(cudaFuncSetAttribute(pairwise_gap_kernel<8>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pairwise_gap_kernel<8><<<dim3(workers, batches), 256, smem, st>>>(
+            bins_dev, ldb, h->n, d, T4, R, P, h->pair_tiles, n_pair_tiles, gap_dev);
+    } else {
+        GR_CUDA_TRY(cudaFuncSetAttribute(pairwise_gap_kernel<4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pairwise_gap_kernel<4><<<dim3(workers, batches), 256, smem, st>>>(
+            bins_dev, ldb, h->n, d, T4, R, P, h->pair_tiles, n_pair_tiles, gap_dev);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)

@@ -6,6 +6,7 @@ the multiplicative-update loop is the CUDA library's gr_nmf_mu_f32 (include/grap
 the NNDSVDa start is computed on the device with torch.linalg (not a hot path, SURVEY.md
 section 8 row B2).
 """
+import os
 from ctypes import byref, c_double, c_int32, c_void_p
 from typing import Optional, Tuple
 
@@ -75,12 +76,17 @@ class NmfSolver:
             raise ValueError('X needs unit column stride; W and H must be contiguous')
         n_iter, err = c_int32(0), c_double(float('nan'))
         err_ptr = byref(err) if (want_error or tol > 0) else None
+        nvtx = os.environ.get('GR_NVTX') == '1'
+        if nvtx:
+            torch.cuda.nvtx.range_push(f'nmf mu n={self.n} f={self.f} r={self.r} <= {max_iter} it')
         with torch.cuda.device(self.device):
             _native.check(self._lib.gr_nmf_mu_f32(
                 self._handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
                 c_void_p(H.data_ptr()), max_iter, float(tol), check_every,
                 1 if use_tf32 else 0, byref(n_iter), err_ptr, _native._stream_ptr(stream)),
                 'gr_nmf_mu_f32')
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         self.last_path = 'tcgen05' if self._lib.gr_nmf_last_path(self._handle) else 'ffma'
         return int(n_iter.value), float(err.value)
 

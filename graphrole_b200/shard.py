@@ -459,7 +459,12 @@ class ShardedRefex:
         if self.C > 1 and self.d * 4 < 128:
             cur = cur.contiguous()
         lo, hi = self.ranges[self.r]
+        nvtx = os.environ.get('GR_NVTX') == '1'      # one range per level for nsys / ncu timelines
         for level in range(levels):
+            if nvtx:
+                if level:
+                    torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push(f'refex level {level + 1} ({self.exchange})')
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
@@ -495,6 +500,8 @@ class ShardedRefex:
                     events.append((e0, e1, e2))
                 cur = nxt
                 last = (self.sums, nxt[lo:hi])
+        if nvtx and levels:
+            torch.cuda.nvtx.range_pop()
         if self.peers is not None:
             # a rank that never arrived at a barrier is an error NOW, not at close(): the replicas
             # would be incomplete

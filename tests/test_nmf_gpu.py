@@ -154,6 +154,41 @@ def test_error_pass_kernels_match_the_oracle(n, f, r, monkeypatch):
     assert got == pytest.approx(simple, rel=2e-6)
 
 
+def test_config5_10m_x_512_at_size():
+    """BASELINE.json configs[4] at its own size: X = 10 M x 512 (5.1e9 entries: every index past
+    2^32), r = 8.  scikit-learn cannot run here in test time, so the checks are the ones that do
+    not depend on size: the tcgen05 pair kernel against the fp32 FFMA kernels from the same
+    start (3 iterations), non-negativity, and the multiplicative update's monotone decrease of
+    ||X - W H||_F (Lee & Seung) -- evaluated by the error pass, itself checked against a float64
+    evaluation on a row sample."""
+    free_gpu, _ = torch.cuda.mem_get_info(0)
+    if free_gpu < 60e9:
+        pytest.skip('needs ~45 GB of HBM')
+    n, f, r = 10_000_000, 512, 8
+    gen = torch.Generator(device='cuda:0').manual_seed(5)
+    X = torch.rand(n, 8, device='cuda:0', generator=gen).square_() @ \
+        torch.rand(8, f, device='cuda:0', generator=gen)
+    X += 0.05 * torch.rand(n, f, device='cuda:0', generator=gen)
+    W0 = torch.rand(n, r, device='cuda:0', generator=gen) + 0.1
+    H0 = torch.rand(r, f, device='cuda:0', generator=gen) + 0.1
+    e0 = factor.nmf_error(X, W0, H0)
+    Wt, Ht, _, et = factor.nmf_mu(X, W0, H0, max_iter=3, tol=0, use_tf32=True)
+    assert factor.last_path == 'tcgen05'
+    Wf, Hf, _, ef = factor.nmf_mu(X, W0, H0, max_iter=3, tol=0, use_tf32=False)
+    assert bool((Wt >= 0).all()) and bool((Ht >= 0).all())
+    assert float((Wt - Wf).abs().max() / Wf.abs().max()) < 5e-3
+    assert float((Ht - Hf).abs().max() / Hf.abs().max()) < 5e-3
+    assert et == pytest.approx(ef, rel=1e-3)
+    assert et < e0
+    W6, H6, _, e6 = factor.nmf_mu(X, Wt, Ht, max_iter=3, tol=0, use_tf32=True)
+    assert e6 < et
+    # the error pass itself, on the last 50 000 rows (indices past 2^32 in the flattened matrix)
+    tail = slice(n - 50_000, n)
+    want = torch.linalg.norm(X[tail].double() - W6[tail].double() @ H6.double()).item()
+    got = factor.nmf_error(X[tail].contiguous(), W6[tail].contiguous(), H6)
+    assert got == pytest.approx(want, rel=1e-6)
+
+
 def test_tensor_core_path_is_taken_and_matches_ffma():
     """Shapes the tcgen05 kernel takes (r % 4 == 0, f % 4 == 0, f <= 1024) must actually run it --
     no silent fallback -- and agree with the FFMA kernels; other shapes report 'ffma'."""

@@ -164,7 +164,8 @@ def test_binning_rejects_bad_arguments():
 # ---- pairwise gaps ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize('n,d', [(1, 2), (5, 3), (100, 4), (1000, 5), (777, 9), (5000, 33),
-                                 (3001, 128), (600, 260)])
+                                 (3001, 63), (3001, 64), (777, 65), (2000, 100), (3001, 128),
+                                 (600, 260), (100, 1024)])
 def test_pairwise_gaps_match_numpy(n, d):
     rng = np.random.RandomState(d)
     bins = rng.randint(0, 12, (d, n)).astype(np.int32)
@@ -176,7 +177,30 @@ def test_pairwise_gaps_match_numpy(n, d):
     p.close()
     want = np.abs(bins[:, None, :].astype(np.int64) - bins[None, :, :]).max(axis=2)
     assert np.array_equal(got, want)
-    assert np.array_equal(got, prune_oracle.chebyshev_gaps(bins)) or d > 40
+    if d <= 40:
+        assert np.array_equal(got, prune_oracle.chebyshev_gaps(bins))
+
+
+def test_pairwise_gaps_tile_sizes_agree(monkeypatch):
+    """From 64 columns on the kernel keeps 8 x 8 pair tiles in registers, below that 4 x 4
+    (GR_PRUNE_TILE4=1 forces 4 x 4): same integers, many rows, ragged column count."""
+    n, d = 400_003, 72
+    g = torch.Generator(device=DEV).manual_seed(9)
+    bins = torch.randint(0, 25, (d, n), device=DEV, generator=g, dtype=torch.int32)
+    bins[70] = bins[3]
+    bins[71, n - 1] += 5000
+    p = _native.Pruner(n, DEV)
+    wide = p.pairwise_gaps(bins)
+    monkeypatch.setenv('GR_PRUNE_TILE4', '1')
+    narrow = p.pairwise_gaps(bins)
+    p.close()
+    assert torch.equal(wide, narrow)
+    assert int(wide[70, 3]) == 0 and int(wide[71].max()) >= 4976
+    sub = bins[:, :5000]
+    want = (sub[:, None, :].long() - sub[None, :, :].long()).abs().amax(dim=2)
+    p = _native.Pruner(5000, DEV)
+    assert torch.equal(p.pairwise_gaps(sub.contiguous()).long(), want)
+    p.close()
 
 
 def test_pairwise_gaps_large_values_and_many_rows():
