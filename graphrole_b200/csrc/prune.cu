@@ -152,8 +152,8 @@ __global__ void pair_tile_table_kernel(int2* table, int T) {
 // P pair slots x S row slices (P = power of two >= min(#pair tiles, 256)): pair tile
 // pt = blockIdx.y + slot * gridDim.y, rows slice, slice + S, ... of every chunk.  A thread keeps
 // the running maxima of a TS x TS block of column pairs in registers: TS = 4 (2 LDS.128 per 16
-// pairs) for narrow frames, TS = 8 (4 LDS.128 per 64 pairs: measured 25.6 -> 18.0 ms for 128
-// columns x 10 M rows, profiles/r2_exp_pairwise_tiles.txt) from 64 columns on.  T4 = number of
+// pairs) for narrow frames, TS = 8 (4 LDS.128 per 64 pairs: measured 29.9 -> 18.4 ms for 128
+// columns x 10 M rows) from 96 columns on.  T4 = number of
 // 4-column groups the chunk holds (even for TS = 8), T = number of TS-column tiles.
 template <int TS>
 __global__ void __launch_bounds__(256, 1)
@@ -359,8 +359,10 @@ extern "C" int gr_prune_pairwise_gap_i32(gr_pruner_t* h, const int32_t* bins_dev
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GR_CUDA_TRY(cudaMemsetAsync(gap_dev, 0, (size_t)d * d * sizeof(int32_t), st));
     if (d == 1) return GR_OK;
-    // 8 x 8 register tiles from 64 columns on (enough pair tiles to fill the slots), 4 x 4 below
-    const int TS = (d >= 64 && !getenv("GR_PRUNE_TILE4")) ? 8 : 4;
+    // 8 x 8 register tiles once there are enough pair tiles to fill the slots, 4 x 4 below
+    // (measured, 10 M rows: 64 columns 4.1 ms with 4 x 4 vs 6.6 ms with 8 x 8; 128 columns 29.9 vs
+    // 18.4 ms; 256 columns 137.6 vs 74.2 ms -- profiles/r2_pairwise_tiles_integrated.txt)
+    const int TS = (d >= 96 && !getenv("GR_PRUNE_TILE4")) ? 8 : 4;
     const int T = ceil_div(d, TS);
     const int T4 = T * (TS / 4);
     const int n_pair_tiles = T * (T + 1) / 2;

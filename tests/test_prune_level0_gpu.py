@@ -164,7 +164,7 @@ def test_binning_rejects_bad_arguments():
 # ---- pairwise gaps ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize('n,d', [(1, 2), (5, 3), (100, 4), (1000, 5), (777, 9), (5000, 33),
-                                 (3001, 63), (3001, 64), (777, 65), (2000, 100), (3001, 128),
+                                 (3001, 64), (3001, 95), (3001, 96), (777, 97), (2000, 100), (3001, 128),
                                  (600, 260), (100, 1024)])
 def test_pairwise_gaps_match_numpy(n, d):
     rng = np.random.RandomState(d)
@@ -182,20 +182,20 @@ def test_pairwise_gaps_match_numpy(n, d):
 
 
 def test_pairwise_gaps_tile_sizes_agree(monkeypatch):
-    """From 64 columns on the kernel keeps 8 x 8 pair tiles in registers, below that 4 x 4
+    """From 96 columns on the kernel keeps 8 x 8 pair tiles in registers, below that 4 x 4
     (GR_PRUNE_TILE4=1 forces 4 x 4): same integers, many rows, ragged column count."""
-    n, d = 400_003, 72
+    n, d = 400_003, 100
     g = torch.Generator(device=DEV).manual_seed(9)
     bins = torch.randint(0, 25, (d, n), device=DEV, generator=g, dtype=torch.int32)
-    bins[70] = bins[3]
-    bins[71, n - 1] += 5000
+    bins[98] = bins[3]
+    bins[99, n - 1] += 5000
     p = _native.Pruner(n, DEV)
     wide = p.pairwise_gaps(bins)
     monkeypatch.setenv('GR_PRUNE_TILE4', '1')
     narrow = p.pairwise_gaps(bins)
     p.close()
     assert torch.equal(wide, narrow)
-    assert int(wide[70, 3]) == 0 and int(wide[71].max()) >= 4976
+    assert int(wide[98, 3]) == 0 and int(wide[99].max()) >= 4976
     sub = bins[:, :5000]
     want = (sub[:, None, :].long() - sub[None, :, :].long()).abs().amax(dim=2)
     p = _native.Pruner(5000, DEV)
