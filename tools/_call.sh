@@ -1,27 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_prune_level0_gpu.py -q > gpurun_out/r2c15_prune.log 2>&1; echo "prune rc=$?"; tail -3 gpurun_out/r2c15_prune.log
-timeout 600 python - > gpurun_out/r2c15_pairwise.txt 2>&1 <<'PY'
-import json, os, sys, torch
-sys.path.insert(0, '.')
-from graphrole_b200 import _native
-dev = torch.device('cuda', 0)
-n = 10_000_000
-def timed(fn, reps=3):
-    fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
-p = _native.Pruner(n, dev)
-for d in (32, 64, 128, 256):
-    bins = torch.randint(0, 24, (d, n), device=dev, dtype=torch.int32)
-    row = {'columns': d, 'ms_default': round(timed(lambda: p.pairwise_gaps(bins)), 3)}
-    os.environ['GR_PRUNE_TILE4'] = '1'
-    row['ms_tile4'] = round(timed(lambda: p.pairwise_gaps(bins)), 3)
-    del os.environ['GR_PRUNE_TILE4']
-    print(json.dumps(row), flush=True)
-    del bins
-PY
-echo "pairwise rc=$?"; cat gpurun_out/r2c15_pairwise.txt
+for dbg in 0 1 2 8 11; do
+  GR_NMF_TC_DEBUG=$dbg timeout 200 python tools/bench_nmf.py --ranks 8,32 --paths tcgen05 --iters 20 > gpurun_out/r2c16_nmf_dbg$dbg.txt 2>&1
+  echo "debug=$dbg: $(grep -o '"r": [0-9]*, "iters": [0-9]*, "ms_per_iter": [0-9.]*' gpurun_out/r2c16_nmf_dbg$dbg.txt | tr '\n' ' ')"
+done
+for ring in "2 2" "3 1"; do
+  set -- $ring
+  GR_NMF_RING_A=$1 GR_NMF_RING_B=$2 timeout 200 python tools/bench_nmf.py --ranks 8,32 --paths tcgen05 --iters 20 > gpurun_out/r2c16_nmf_ring$1$2.txt 2>&1
+  echo "rings $1/$2: $(grep -o '"r": [0-9]*, "iters": [0-9]*, "ms_per_iter": [0-9.]*' gpurun_out/r2c16_nmf_ring$1$2.txt | tr '\n' ' ')"
+done
+GR_NMF_RING_A=3 GR_NMF_RING_B=1 GR_NMF_TC_DEBUG=11 timeout 200 python tools/bench_nmf.py --ranks 8 --paths tcgen05 --iters 20 > gpurun_out/r2c16_nmf_ring31_dbg11.txt 2>&1
+echo "rings 3/1 debug=11: $(grep -o '"r": [0-9]*, "iters": [0-9]*, "ms_per_iter": [0-9.]*' gpurun_out/r2c16_nmf_ring31_dbg11.txt | tr '\n' ' ')"
