@@ -644,10 +644,10 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             if (do_store) {
                 tma_store_2d(&map_w, 0, row, w_sub(wb));
                 tma_store_commit();
-                if constexpr (CL == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+                if constexpr (CL == 1) tma_store_wait_read<0>();
             }
+            // CTA pair: the refill is issued at the START of the next epilogue iteration (below)
             if constexpr (CL == 1) load_w_sub(i + 2);
-            else if (i >= 1) load_w_sub(i + 2);
         };
         if constexpr (CL == 1) {
             for (int64_t i = 0; i < nb; ++i) {
@@ -701,6 +701,16 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             for (int64_t jj = 0; jj <= nb; ++jj) {
                 const int64_t i = jj - 1;                    // block of steps (1) and (3)
                 if (q == 0 && lane == 0 && jj < nb) GR_TRACE(3, jj, 0);
+                // Refill the W tile buffer of block i - 1 (its store was issued at the end of the
+                // previous iteration) with block i + 2 BEFORE this iteration's waits and its W
+                // update: issued after the update, the tile of block i + 2 trailed WFULL(i) by a
+                // TMA round trip and the MMA thread spun on WINFULL in every block -- the W tile
+                // load sat on the loop-carried chain load -> P1' -> D1FULL -> exchange -> update
+                // -> load (the kernel took 4.0 ms per C5 iteration even with every MMA skipped).
+                if (i >= 1 && lane == 0) {
+                    tma_store_wait_read<0>();
+                    load_w_sub(i + 2);
+                }
                 if (i >= 0) {
                     const int b = (int)(i % 3);
                     mbar_wait_acquire_cluster(bar(B_XCHFULL + b), (uint32_t)((i / 3) & 1));
@@ -999,8 +1009,11 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     p.cluster = s->cluster;
     // wide P2 needs two 128-column tiles per CTA in a two-stage ring (so that a block's tiles sit
     // side by side in shared memory) and 256 TMEM columns behind the D1 / Den / W^T W buffers
+    // Opt-in (GR_NMF_WIDE_P2=1): measured on C5 after the early W refill, 16 MMAs of M = 128 x
+    // N = 32 (4.14 / 4.29 / 4.33 / 4.36 ms for r = 4 / 8 / 16 / 32) beat 8 of M = 64 x N = 256
+    // (4.24 / 4.33 / 4.37 / 4.62 ms): an M = 64 MMA runs the tensor pipe at half rate.
     p.wide_p2 = s->cluster == 2 && groups == 4 && s->ring_b == 2 && kP2M == 128 &&
-                col_d2(3) + 256 <= kTmemCols && !getenv("GR_NMF_NARROW_P2");
+                col_d2(3) + 256 <= kTmemCols && getenv("GR_NMF_WIDE_P2") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)s->grid);
     cfg.blockDim = dim3(kThreads);
