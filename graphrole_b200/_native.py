@@ -69,6 +69,8 @@ SIGNATURES = {
                                        c_void_p]),
     'gr_nmf_error_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  POINTER(c_double), c_void_p]),
+    'gr_nmf_error_tf32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                  POINTER(c_double), c_void_p]),
     'gr_quantizer_create': (c_int, [POINTER(c_void_p), c_int64, c_int]),
     'gr_quantizer_destroy': (c_int, [c_void_p]),
     'gr_quantizer_bind_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

@@ -37,6 +37,9 @@ int nmf_error(gr_nmf* h, const float* X, int64_t ldx, const float* W, const floa
 // tcgen05 / TMA fused single-pass iteration (nmf_mu_tc.cu)
 bool nmf_tc_supported(const gr_nmf* h, const float* X, int64_t ldx);
 int nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float* H, cudaStream_t st);
+// ||X - W H||_F with W H on the tensor core (TF32 operands, fp32 residual, fp64 sums)
+int nmf_error_tc(gr_nmf* h, const float* X, int64_t ldx, const float* W, const float* H,
+                 double* err, cudaStream_t st);
 void nmf_tc_release(gr_nmf* h);
 
 }  // namespace gr

@@ -505,6 +505,18 @@ extern "C" int gr_nmf_error_f32(gr_nmf_t* h, const float* X, int64_t ldx, const 
     return nmf_error(h, X, ldx, W, H, err_out, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int gr_nmf_error_tf32(gr_nmf_t* h, const float* X, int64_t ldx, const float* W,
+                                 const float* H, double* err_out, void* stream) {
+    GR_REQUIRE(h && X && W && H && err_out, "gr_nmf_error_tf32: NULL argument");
+    GR_REQUIRE(ldx >= h->f, "gr_nmf_error_tf32: ldx < f");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    GR_REQUIRE(nmf_tc_supported(h, X, ldx),
+               "gr_nmf_error_tf32: shape not taken by the tensor-core kernels (r <= 32, r %% 4 == 0, "
+               "f %% 4 == 0, 16-byte aligned rows); use gr_nmf_error_f32");
+    return nmf_error_tc(h, X, ldx, W, H, err_out, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int gr_nmf_mu_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W, float* H,
                              int32_t max_iter, double tol, int32_t check_every, int32_t use_tf32,
                              int32_t* n_iter_out, double* err_out, void* stream) {
@@ -516,6 +528,14 @@ extern "C" int gr_nmf_mu_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     const bool tc = use_tf32 && nmf_tc_supported(h, X, ldx);
+    // the convergence checks follow the path of the iteration: W H on the tensor core beside the
+    // tcgen05 iteration kernel (GR_NMF_ERROR_FFMA=1 keeps them on the fp32 FFMA pass)
+    static const bool err_ffma = getenv("GR_NMF_ERROR_FFMA") != nullptr;
+    auto nmf_error = [&](gr_nmf* hh, const float* Xp, int64_t ld, const float* Wp, const float* Hp,
+                         double* e, cudaStream_t s) {
+        return tc && !err_ffma ? nmf_error_tc(hh, Xp, ld, Wp, Hp, e, s)
+                               : gr::nmf_error(hh, Xp, ld, Wp, Hp, e, s);
+    };
     double error_at_init = 0.0, previous = 0.0, error = 0.0;
     if (tol > 0) {
         if (int rc = nmf_error(h, X, ldx, W, H, &error_at_init, st)) return rc;

@@ -59,6 +59,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -112,6 +113,7 @@ struct TcParams {
     int wide_p2;         // P2 as 8 MMAs of M = 64 (roles) x N = 256 (all columns of the CTA) per block
     int debug;           // development switches (GR_NMF_TC_DEBUG): 1 skip P1 MMAs, 2 skip P2 MMAs,
                          // 8 skip P2 TMA loads + MMAs (results are then meaningless: timing only)
+    int full_n;          // development (GR_NMF_FULL_N): UMMA N = 32 whatever r is
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -289,13 +291,12 @@ __host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo, uint64_t layout) {
 }
 // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit
 // 16 (1 = MN-major), N >> 3 [17,23), M >> 4 [24,29)
-constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-constexpr uint32_t kIdescP1 = make_idesc(64, kRP, 0, 0);    // X K-major, H K-major
-constexpr uint32_t kIdescP2 = make_idesc(kP2M, kRP, 1, 1);    // X^T MN-major, W_b MN-major
-constexpr uint32_t kIdescWtW = make_idesc(64, kRP, 1, 1);   // W_b MN-major on both sides
+// P1 / P1': make_idesc(64, N, 0, 0) (X K-major, H K-major); P2: make_idesc(128, N, 1, 1) (X^T and
+// W_b MN-major); W^T W: make_idesc(64, N, 1, 1) -- N follows the number of roles, see the MMA warp
 // wide P2: (W^T X)[roles, columns] = W_b^T (MN-major, M = 64: roles 32..63 alias 0..31) . X_b
 // (MN-major, N = 256 columns = both P2 stages of the block, which are adjacent in the ring)
 constexpr uint32_t kIdescP2Wide = make_idesc(64, 256, 1, 1);
@@ -458,6 +459,14 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
             // with 128 KB of ring space the slot turn-around bounds both streams, and blocking
             // mbarrier waits have less latency than a polling loop.
             uint32_t ita = 0, itb = 0;
+            // UMMA N = the roles actually present, rounded up to the instruction's granularity
+            // (8 at M = 64, 16 at M = 128): the B operands (H, H H^T, W_b) are read from shared
+            // memory for every MMA, and columns r.. of every accumulator are never used.
+            const int n1 = p.full_n ? kRP : (p.r + 7) & ~7, n2 = p.full_n ? kRP : (p.r + 15) & ~15;
+            const uint32_t idesc_p1 = make_idesc(64, n1, 0, 0);
+            const uint32_t idesc_p2 = make_idesc(kP2M, kP2M == 128 ? n2 : n1, 1, 1);
+            const uint32_t idesc_wtw = make_idesc(64, n1, 1, 1);
+            const int k_den = p.full_n ? 4 : (p.r + 7) >> 3;   // W_b has zero columns from r on
             for (int64_t i = 0; i < nb + LAG; ++i) {
                 const bool do_p1 = i < nb, do_p2 = i >= LAG;
                 const int buf1 = (int)(i % NBUF);        // D1 / Den buffer of block i
@@ -484,7 +493,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                                 for (int k = 0; k < 4; ++k)
                                     tc_mma_tf32_split(d1, a_lo + (c * kBoxBytes + k * 32) / 16, hi,
                                                       b_lo + (c * kHBoxBytes + k * 32) / 16, hi,
-                                                      kIdescP1, (uint32_t)(g | c | k));
+                                                      idesc_p1, (uint32_t)(g | c | k));
                         }
                         tc_commit(bar(B_EMPTY_A + st));
                     }
@@ -498,8 +507,9 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
                         constexpr uint32_t hi = desc_hi(1024, kLayoutSw128);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc_mma_tf32_split(tmem + kColDen + buf1 * kRP, a_lo + k * 2, hi,
-                                              b_lo + k * 2, hi, kIdescP1, (uint32_t)k);
+                            if (k < k_den)
+                                tc_mma_tf32_split(tmem + kColDen + buf1 * kRP, a_lo + k * 2, hi,
+                                                  b_lo + k * 2, hi, idesc_p1, (uint32_t)k);
                     }
                     tc_commit(bar(B_D1FULL + buf1));
                     GR_TRACE(2, i, 2);
@@ -547,7 +557,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
                                 tc_mma_tf32_split(tmem + kColD2 + t * kRP, a_lo + k * 64, hi,
-                                                  b_lo + k * 64, hi, kIdescP2, acc0 | (uint32_t)k);
+                                                  b_lo + k * 64, hi, idesc_p2, acc0 | (uint32_t)k);
                         }
                         tc_commit(bar(B_EMPTY_B + st));
                     }
@@ -562,7 +572,7 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             tc_mma_tf32_split(tmem + kColWtW, d_lo + k * 64, hi, d_lo + k * 64, hi,
-                                              kIdescWtW, acc0 | (uint32_t)k);
+                                              idesc_wtw, acc0 | (uint32_t)k);
                     }
                     tc_commit(bar(B_WEMPTY));
                     GR_TRACE(2, j, 4);
@@ -822,6 +832,203 @@ nmf_fused_tc_kernel(const __grid_constant__ CUtensorMap map_x_k,
     }
 }
 
+// ---- convergence check on the tensor core: ||X - W H||_F^2 ------------------------------------
+// sklearn evaluates the dense residual every 10 iterations (_nmf.py:867-879 -> :122).  On CUDA
+// cores that pass is bound by FFMA issue (n f r FMAs: 10.8 ms on C5 at r = 32 against 3.5 ms for
+// streaming X once, nmf_mu.cu).  Here W_b H runs as tcgen05.mma (M = 128 rows, N = 64 columns,
+// K = 8 roles x ceil(r / 8)) into TMEM, and the epilogue warps only subtract and square:
+//   warp 0     TMA producer: H^T of the CTA's 256-column span once (B operand, K-major), per
+//              128-row block the W tile (A operand, K-major), per stage two [128 x 32] boxes of X
+//              (plain fp32: X never passes through the tensor core)
+//   warp 1     MMA issuer: one accumulator of 64 TMEM columns per stage, four in rotation
+//   warps 2-9  epilogue: lane quarter warp % 4, column half (warp - 2) / 4; thread = one row x 32
+//              columns: tcgen05.ld.32x32b, eight conflict-free LDS.128 of the swizzled X box,
+//              fp32 partial per stage (32 terms), fp64 running total per thread
+// W and H^T are loaded with the TFLOAT32 element type (round to nearest; W is already held at
+// tf32 precision by the iteration kernel), so the only perturbation is the rounding of H: the
+// error moves by ~1e-7 relative on the C5 data (tests/test_nmf_gpu.py states 1e-5).
+// CTA c works on column span c % spans of the row blocks c / spans, c / spans + grid / spans, ...
+// Partials: out[8 * CTA + epilogue warp], summed by the host in that order.
+constexpr int kErrTcThreads = 320;
+constexpr int kErrTcRows = 128;                              // rows per block = UMMA M
+constexpr int kErrTcChunk = 64;                              // columns per stage = UMMA N
+constexpr int kErrTcSpan = 256;                              // columns per CTA
+constexpr int kErrTcBoxBytes = kErrTcRows * kBoxCols * 4;    // 16 KB: [128 rows x 32 columns] of X
+constexpr int kErrTcStageBytes = 2 * kErrTcBoxBytes;         // 32 KB
+constexpr int kErrTcWBytes = kErrTcRows * kRP * 4;           // 16 KB
+constexpr int kErrTcHtBytes = kErrTcSpan * kRP * 4;          // 32 KB
+constexpr int kErrTcStages = 5, kErrTcDBufs = 4;
+constexpr uint32_t kErrTcSmem = kErrTcHtBytes + 2 * kErrTcWBytes + kErrTcStages * kErrTcStageBytes +
+                                64 * 8 + 1024;
+enum { E_FULL = 0, E_EMPTY = 5, E_HFULL = 10, E_WFULL = 11, E_WEMPTY = 13, E_DFULL = 15,
+       E_DEMPTY = 19, E_COUNT = 23 };
+
+struct ErrTcParams {
+    int64_t n_blocks;    // ceil(n / 128)
+    int f, r;
+    int spans;           // ceil(f / 256)
+    double* out;         // [grid, 8]
+};
+
+__global__ void nmf_transpose_h_kernel(const float* __restrict__ H, int r, int f,
+                                       float* __restrict__ Ht) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // Ht[col][role], 32 roles per column
+    if (i >= f * kRP) return;
+    const int col = i / kRP, role = i % kRP;
+    Ht[i] = role < r ? H[(int64_t)role * f + col] : 0.f;
+}
+
+__global__ void __launch_bounds__(kErrTcThreads, 1)
+nmf_error_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                    const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_ht, const ErrTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t s_ht = smem_u32(smem), s_w = s_ht + kErrTcHtBytes;
+    const uint32_t s_ring = s_w + 2 * kErrTcWBytes;
+    const uint32_t s_bars = s_ring + kErrTcStages * kErrTcStageBytes;
+    auto bar = [&](int slot) { return s_bars + 8u * (uint32_t)slot; };
+    __shared__ uint32_t tmem_ptr_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int span = (int)blockIdx.x % p.spans;
+    const int64_t first = blockIdx.x / p.spans, stride = gridDim.x / p.spans;
+    const int64_t nb = (p.n_blocks - first + stride - 1) / stride;
+    const int col_lo = span * kErrTcSpan;
+    const int cols = min(p.f - col_lo, kErrTcSpan);
+    const int nch = (cols + kErrTcChunk - 1) / kErrTcChunk;      // stages per row block
+    const int nboxes = (cols + kBoxCols - 1) / kBoxCols;         // 32-column boxes that hold data
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kErrTcStages; ++s) {
+            mbar_init(bar(E_FULL + s), 1);
+            mbar_init(bar(E_EMPTY + s), 8);
+        }
+        mbar_init(bar(E_HFULL), 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar(E_WFULL + b), 1); mbar_init(bar(E_WEMPTY + b), 1); }
+        for (int b = 0; b < kErrTcDBufs; ++b) {
+            mbar_init(bar(E_DFULL + b), 1);
+            mbar_init(bar(E_DEMPTY + b), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_ptr_s)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tmem_ptr_s != 0) __trap();      // all 512 columns: the allocation starts at 0
+    constexpr uint32_t tmem = 0;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar(E_HFULL), (uint32_t)nboxes * kHBoxBytes);
+            for (int b = 0; b < nboxes; ++b)
+                tma_load_2d(s_ht + b * kHBoxBytes, &map_ht, 0, col_lo + b * kBoxCols, bar(E_HFULL));
+            uint32_t it = 0;
+            for (int64_t i = 0; i < nb; ++i) {
+                const int row = (int)((first + i * stride) * kErrTcRows);
+                const int wb = (int)(i & 1);
+                mbar_wait(bar(E_WEMPTY + wb), (uint32_t)(((i >> 1) & 1) ^ 1));
+                mbar_expect_tx(bar(E_WFULL + wb), kErrTcWBytes);
+                tma_load_2d(s_w + wb * kErrTcWBytes, &map_w, 0, row, bar(E_WFULL + wb));
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int st = it % kErrTcStages;
+                    mbar_wait(bar(E_EMPTY + st), ((it / kErrTcStages) & 1) ^ 1);
+                    const int nh = min(2, nboxes - 2 * c);
+                    mbar_expect_tx(bar(E_FULL + st), (uint32_t)nh * kErrTcBoxBytes);
+                    for (int hf = 0; hf < nh; ++hf)
+                        tma_load_2d(s_ring + st * kErrTcStageBytes + hf * kErrTcBoxBytes, &map_x,
+                                    col_lo + c * kErrTcChunk + hf * kBoxCols, row,
+                                    bar(E_FULL + st));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            mbar_wait(bar(E_HFULL), 0);
+            tc_fence_after();
+            const int ks = (p.r + 7) >> 3;          // W and H^T hold zeros from role r on
+            constexpr uint32_t idesc = make_idesc(kErrTcRows, kErrTcChunk, 0, 0);
+            constexpr uint32_t hi = desc_hi(1024, kLayoutSw128);
+            uint32_t it = 0;
+            for (int64_t i = 0; i < nb; ++i) {
+                const int wb = (int)(i & 1);
+                mbar_wait(bar(E_WFULL + wb), (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                const uint32_t a_lo = desc_lo(s_w + wb * kErrTcWBytes, 16);
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int db = it % kErrTcDBufs;
+                    mbar_wait(bar(E_DEMPTY + db), ((it / kErrTcDBufs) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_lo = desc_lo(s_ht + c * 2 * kHBoxBytes, 16);
+                    for (int k = 0; k < ks; ++k)
+                        tc_mma_tf32_split(tmem + db * kErrTcChunk, a_lo + k * 2, hi, b_lo + k * 2,
+                                          hi, idesc, (uint32_t)k);
+                    tc_commit(bar(E_DFULL + db));
+                }
+                tc_commit(bar(E_WEMPTY + wb));
+            }
+        }
+    } else {
+        const int q = warp & 3, hf = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int k = q * 32 + lane;                 // this thread's row of the block
+        double total = 0.0;
+        uint32_t it = 0;
+        for (int64_t i = 0; i < nb; ++i)
+            for (int c = 0; c < nch; ++c, ++it) {
+                const int st = it % kErrTcStages, db = it % kErrTcDBufs;
+                // Both waits also in a warp whose column half holds no data (ragged span): a warp
+                // that ran ahead would arrive twice within one phase of the EMPTY barriers.
+                mbar_wait(bar(E_DFULL + db), (it / kErrTcDBufs) & 1);
+                mbar_wait(bar(E_FULL + st), (it / kErrTcStages) & 1);
+                if (hf < min(2, nboxes - 2 * c)) {
+                    tc_fence_after();
+                    float wh[32];
+                    tc_ld_32x32(tmem + lane_base + db * kErrTcChunk + hf * kBoxCols, wh);
+                    tc_fence_before();
+                    // row k of the box: 128 bytes, 16-byte chunk j at position j ^ (k % 8)
+                    const uint32_t xr = s_ring + st * kErrTcStageBytes + hf * kErrTcBoxBytes + k * 128;
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                     : "r"(xr + ((j ^ (k & 7)) << 4)));
+                        const float d0 = x.x - wh[4 * j], d1 = x.y - wh[4 * j + 1];
+                        const float d2 = x.z - wh[4 * j + 2], d3 = x.w - wh[4 * j + 3];
+                        p0 = fmaf(d0, d0, p0);
+                        p1 = fmaf(d1, d1, p1);
+                        p2 = fmaf(d2, d2, p2);
+                        p3 = fmaf(d3, d3, p3);
+                    }
+                    total += (double)((p0 + p1) + (p2 + p3));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(E_DEMPTY + db));
+                    mbar_arrive(bar(E_EMPTY + st));
+                }
+            }
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (lane == 0) p.out[(int64_t)blockIdx.x * 8 + (warp - 2)] = total;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 struct TcState {
     int grid = 0;
@@ -835,6 +1042,13 @@ struct TcState {
     const float* X = nullptr;   // what the X maps were encoded for
     int64_t ldx = 0;
     const float* H = nullptr;
+    // convergence check (nmf_error_tc)
+    CUtensorMap map_ex, map_ew, map_eht;
+    float* d_ht = nullptr;      // [f, 32]: H transposed, zero from role r on
+    const float* eX = nullptr;
+    int64_t eldx = 0;
+    const float* eW = nullptr;
+    bool err_ready = false;
 };
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -910,6 +1124,8 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
         s = new (std::nothrow) TcState();
         if (!s) return fail(GR_ERR_OUT_OF_MEMORY, "nmf tc state");
         h->tc_state = s;
+    }
+    if (!s->grid) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const int64_t n_blocks = ceil_div<int64_t>(h->n, kBlockRows);
@@ -1007,6 +1223,7 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     }
     p.debug = getenv("GR_NMF_TC_DEBUG") ? atoi(getenv("GR_NMF_TC_DEBUG")) : 0;
     p.cluster = s->cluster;
+    p.full_n = getenv("GR_NMF_FULL_N") != nullptr;
     // wide P2 needs two 128-column tiles per CTA in a two-stage ring (so that a block's tiles sit
     // side by side in shared memory) and 256 TMEM columns behind the D1 / Den / W^T W buffers
     // Opt-in (GR_NMF_WIDE_P2=1): measured on C5 after the early W refill, 16 MMAs of M = 128 x
@@ -1057,9 +1274,72 @@ int gr::nmf_iteration_tc(gr_nmf* h, const float* X, int64_t ldx, float* W, float
     return nmf_finish_iteration(h, s->d_part_wtx, s->d_part_wtw, s->grid, kRP, H, st);
 }
 
+// ||X - W H||_F on the tensor core (nmf_error_tc_kernel); same shapes as nmf_tc_supported.
+int gr::nmf_error_tc(gr_nmf* h, const float* X, int64_t ldx, const float* W, const float* H,
+                     double* err, cudaStream_t st) {
+    TcState* s = static_cast<TcState*>(h->tc_state);
+    if (!s) {
+        s = new (std::nothrow) TcState();
+        if (!s) return fail(GR_ERR_OUT_OF_MEMORY, "nmf tc state");
+        h->tc_state = s;
+    }
+    if (!s->err_ready) {
+        GR_CUDA_TRY(cudaMalloc(&s->d_ht, (size_t)h->f * kRP * sizeof(float)));
+        GR_CUDA_TRY(cudaFuncSetAttribute(nmf_error_tc_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kErrTcSmem));
+        if (int rc = encode_2d(&s->map_eht, s->d_ht, (uint64_t)kRP, (uint64_t)h->f,
+                               (uint64_t)kRP * 4, kRP, kBoxCols, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
+        s->err_ready = true;
+    }
+    if (s->eX != X || s->eldx != ldx) {
+        // plain fp32: X is read by the epilogue threads, not by the tensor core
+        if (int rc = encode_2d(&s->map_ex, X, (uint64_t)h->f, (uint64_t)h->n, (uint64_t)ldx * 4,
+                               kBoxCols, kErrTcRows, CU_TENSOR_MAP_SWIZZLE_128B, true))
+            return rc;
+        s->eX = X;
+        s->eldx = ldx;
+    }
+    if (s->eW != W) {
+        if (int rc = encode_2d(&s->map_ew, W, (uint64_t)h->r, (uint64_t)h->n, (uint64_t)h->r * 4,
+                               kRP, kErrTcRows, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
+        s->eW = W;
+    }
+    nmf_transpose_h_kernel<<<ceil_div(h->f * kRP, 256), 256, 0, st>>>(H, h->r, h->f, s->d_ht);
+    count_launch();
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    ErrTcParams p;
+    p.n_blocks = ceil_div<int64_t>(h->n, kErrTcRows);
+    p.f = h->f;
+    p.r = h->r;
+    p.spans = ceil_div(h->f, kErrTcSpan);
+    p.out = h->d_err_part;
+    const int streams = (int)std::min<int64_t>(std::max(1, sms / p.spans), p.n_blocks);
+    const int grid = streams * p.spans;
+    nmf_error_tc_kernel<<<grid, kErrTcThreads, kErrTcSmem, st>>>(s->map_ex, s->map_ew, s->map_eht,
+                                                                p);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(GR_ERR_CUDA, "nmf_error_tc_kernel launch failed: %s", cudaGetErrorString(e));
+    const size_t cnt = (size_t)grid * 8;
+    h->h_err_part.resize(cnt);
+    GR_CUDA_TRY(cudaMemcpyAsync(h->h_err_part.data(), h->d_err_part, cnt * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
+    double total = 0.0;
+    for (size_t i = 0; i < cnt; ++i) total += h->h_err_part[i];  // fixed order
+    *err = std::sqrt(total);
+    return GR_OK;
+}
+
 void gr::nmf_tc_release(gr_nmf* h) {
     TcState* s = static_cast<TcState*>(h->tc_state);
     if (!s) return;
+    cudaFree(s->d_ht);
     cudaFree(s->d_part_wtx);
     cudaFree(s->d_part_wtw);
     delete s;

@@ -131,8 +131,9 @@ def nmf_mu(X: torch.Tensor, W0: torch.Tensor, H0: torch.Tensor, max_iter: int = 
     return W, H, n_iter, err
 
 
-def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor) -> float:
-    """||X - W H||_F evaluated by the library (dense residual, fp64 accumulation)."""
+def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor, use_tf32: bool = False) -> float:
+    """||X - W H||_F evaluated by the library (dense residual, fp64 accumulation).  use_tf32:
+    the tensor-core form the multiplicative-update loop uses for its convergence checks."""
     n, f = X.shape
     r = W.shape[1]
     lib = _native.load()
@@ -144,10 +145,11 @@ def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor) -> float:
                       'gr_nmf_create')
         try:
             err = c_double(0.0)
-            _native.check(lib.gr_nmf_error_f32(
+            fn = lib.gr_nmf_error_tf32 if use_tf32 else lib.gr_nmf_error_f32
+            _native.check(fn(
                 handle, c_void_p(X.data_ptr()), X.stride(0), c_void_p(W.data_ptr()),
                 c_void_p(H.data_ptr()), byref(err), _native._stream_ptr(None)),
-                'gr_nmf_error_f32')
+                'gr_nmf_error_tf32' if use_tf32 else 'gr_nmf_error_f32')
         finally:
             lib.gr_nmf_destroy(handle)
     return float(err.value)

@@ -209,6 +209,12 @@ int gr_nmf_last_path(const gr_nmf_t* h);
 /* Frobenius error ||X - W H||_F (dense-residual form, _nmf.py:122), fp64 accumulation. */
 int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                      const float* W_dev, const float* H_dev, double* err_out, void* stream);
+/* The same quantity with W H formed on the tcgen05 tensor cores (W and H rounded to TF32, the
+ * residual X - W H and its square in fp32, fp64 sums): the form gr_nmf_mu_f32 uses for its
+ * convergence checks when use_tf32 != 0.  GR_ERR_INVALID_ARGUMENT for shapes the tensor-core
+ * kernels do not take (see gr_nmf_last_path). */
+int gr_nmf_error_tf32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
+                      const float* W_dev, const float* H_dev, double* err_out, void* stream);
 
 /* ---- "next" rows of the path: what runs between the levels -------------
  *

@@ -154,6 +154,57 @@ def test_error_pass_kernels_match_the_oracle(n, f, r, monkeypatch):
     assert got == pytest.approx(simple, rel=2e-6)
 
 
+def tf32_error_bound(want, W, H):
+    """How far the TF32 rounding of the operands may move ||X - W H||_F.  Every term of W H is
+    perturbed by <= 2^-11 relative and without bias: ||delta|| <= dn = 2^-11 ||W H||_F, and
+    ||d + delta|| - ||d|| ~ (d . delta) / ||d|| + ||delta||^2 / (2 ||d||) with d . delta a sum of
+    n f zero-mean terms.  1e-5 relative on top (fp32 residuals, accumulation order)."""
+    W, H = np.asarray(W, dtype=np.float64), np.asarray(H, dtype=np.float64)
+    dn = 2.0 ** -11 * np.linalg.norm(W @ H)
+    return 1e-5 * want + 3 * dn / np.sqrt(W.shape[0] * H.shape[1]) + dn * dn / (2 * want)
+
+
+@pytest.mark.parametrize('n,f,r', [(1, 4, 4), (127, 32, 4), (129, 36, 8), (257, 512, 32),
+                                   (1000, 132, 20), (5003, 96, 12), (4096, 768, 16),
+                                   (3000, 1024, 32), (777, 260, 28), (300, 64, 4),
+                                   (128 * 148 * 2 + 131, 512, 8)])
+def test_tensor_core_error_pass_matches_the_oracle(n, f, r):
+    """gr_nmf_error_tf32 -- W H on tcgen05 (M = 128 row blocks x 64-column stages), residual and
+    squares in fp32, fp64 sums: the convergence check of the default (TF32) product path.
+    Against the float64 oracle (sklearn _nmf.py:114-127) evaluated on the same fp32 inputs,
+    within tf32_error_bound: 1e-5 ... 2e-5 relative from 10^5 entries on (measured on C5: 2e-8
+    against the fp32 FFMA pass), looser only on toy sizes and on (near-)exact fits, where the
+    operand rounding is all that is left of the residual.  Shapes: ragged row blocks (n % 128),
+    ragged 32-column boxes, 64-column stages and 256-column spans (f = 36, 132, 260), one to
+    four spans, several blocks per CTA."""
+    rng = np.random.RandomState(n % 89 + f + r)
+    X, W, H = rng.rand(n, f), rng.rand(n, r), rng.rand(r, f)
+    X32, W32, H32 = (a.astype(np.float32) for a in (X, W, H))
+    want = oracle.frobenius_error(X32.astype(np.float64), W32.astype(np.float64),
+                                  H32.astype(np.float64))
+    got = factor.nmf_error(dev(X32), dev(W32), dev(H32), use_tf32=True)
+    assert abs(got - want) <= tf32_error_bound(want, W32, H32)
+    if n * f >= 100_000:
+        assert got == pytest.approx(want, rel=2e-5)
+    # a fitted model (small residual: the regime of the stopping rule)
+    Wd, Hd, _, _ = factor.nmf_mu(dev(X32), dev(W32), dev(H32), max_iter=30, tol=0, use_tf32=True)
+    Wn, Hn = Wd.double().cpu().numpy(), Hd.double().cpu().numpy()
+    want = oracle.frobenius_error(X32.astype(np.float64), Wn, Hn)
+    got = factor.nmf_error(dev(X32), Wd, Hd, use_tf32=True)
+    assert abs(got - want) <= tf32_error_bound(want, Wn, Hn)
+    if n * f >= 100_000:
+        assert got == pytest.approx(want, rel=2e-5)
+    assert factor.nmf_error(dev(X32), Wd, Hd) == pytest.approx(want, rel=1e-5)
+
+
+def test_tensor_core_error_pass_refuses_other_shapes():
+    X, W, H = torch.rand(50, 130, device='cuda:0'), torch.rand(50, 5, device='cuda:0'), \
+        torch.rand(5, 130, device='cuda:0')
+    with pytest.raises(ValueError):
+        factor.nmf_error(X, W, H, use_tf32=True)
+    assert factor.nmf_error(X, W, H) > 0
+
+
 def test_config5_10m_x_512_at_size():
     """BASELINE.json configs[4] at its own size: X = 10 M x 512 (5.1e9 entries: every index past
     2^32), r = 8.  scikit-learn cannot run here in test time, so the checks are the ones that do
@@ -187,6 +238,11 @@ def test_config5_10m_x_512_at_size():
     want = torch.linalg.norm(X[tail].double() - W6[tail].double() @ H6.double()).item()
     got = factor.nmf_error(X[tail].contiguous(), W6[tail].contiguous(), H6)
     assert got == pytest.approx(want, rel=1e-6)
+    got = factor.nmf_error(X[tail].contiguous(), W6[tail].contiguous(), H6, use_tf32=True)
+    assert got == pytest.approx(want, rel=1e-5)
+    # both forms on the whole matrix (the tensor-core pass is what the loop's checks run)
+    assert factor.nmf_error(X, W6, H6, use_tf32=True) == pytest.approx(
+        factor.nmf_error(X, W6, H6), rel=1e-5)
 
 
 def test_tensor_core_path_is_taken_and_matches_ffma():

@@ -20,6 +20,10 @@ import bench
 from graphrole_b200 import _native
 from graphrole_b200.roles import factor
 
+# development only: time a kernel variant built by tools/build_variant.sh
+if os.environ.get('GR_EXP_LIB'):
+    _native.LIB_PATH = os.path.abspath(os.environ['GR_EXP_LIB'])
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -53,6 +57,21 @@ def main():
             launches = _native.launch_count() - l0
             ms = e0.elapsed_time(e1) / iters
             _, err = solver.update(X, W, H, max_iter=0, tol=0, use_tf32=use_tf32, want_error=True)
+            # one convergence check alone (max_iter = 0, tol > 0: only the error at init runs),
+            # and sklearn's schedule: 20 iterations with a check every 10
+            solver.update(X, W, H, max_iter=0, tol=1e-30, use_tf32=use_tf32)
+            e0.record()
+            for _ in range(3):
+                solver.update(X, W, H, max_iter=0, tol=1e-30, use_tf32=use_tf32)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_check = e0.elapsed_time(e1) / 3
+            e0.record()
+            n_it, err_c = solver.update(X, W, H, max_iter=20, tol=1e-30, check_every=10,
+                                        use_tf32=use_tf32)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_checked = e0.elapsed_time(e1) / max(n_it, 1)
             alg_bytes = args.n * args.f * 4 + 2 * args.n * r * 4
             flops = 4 * args.n * args.f * r + 4 * args.n * r * r + 2 * r * r * args.f
             print(json.dumps({
@@ -60,7 +79,11 @@ def main():
                 'ms_per_iter': round(ms, 3), 'alg_GBps': round(alg_bytes / ms / 1e6, 1),
                 'frac_of_hbm_peak': round(alg_bytes / ms / 1e6 / peak, 3), 'peak': peak,
                 'alg_TFLOPs': round(flops / ms / 1e9, 2), 'error': err,
-                'launches_per_iter': launches / iters}), flush=True)
+                'launches_per_iter': launches / iters, 'ms_per_check': round(ms_check, 3),
+                'ms_per_iter_with_checks': round(ms_checked, 3), 'iters_with_checks': n_it,
+                'error_at_check': err_c,
+                'error_pass': 'ffma' if os.environ.get('GR_NMF_ERROR_FFMA') or not use_tf32
+                else 'tcgen05'}), flush=True)
             solver.close()
             del W, H
         del W0, H0

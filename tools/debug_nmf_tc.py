@@ -8,7 +8,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
+from graphrole_b200 import _native
 from graphrole_b200.roles import factor
+
+if os.environ.get('GR_EXP_LIB'):     # a kernel variant built by tools/build_variant.sh
+    _native.LIB_PATH = os.path.abspath(os.environ['GR_EXP_LIB'])
 
 shapes = [(64, 128, 32), (64, 128, 8), (128, 128, 32), (200, 128, 5), (1000, 512, 32),
           (64 * 148 * 3 + 17, 512, 32), (5000, 96, 12), (4096, 768, 16), (300, 64, 4)]
