@@ -22,6 +22,11 @@ struct gr_nmf {
     std::vector<double> h_err_part;
     bool last_path_tc = false;
     void* tc_state = nullptr;    // owned by nmf_mu_tc.cu
+    // r % 4 != 0 on the tensor-core path: rows of W [n, r] are not 16-byte multiples (TMA), so
+    // the loop runs on zero-padded factors of rank r4 = r rounded up to 4 (nmf_mu.cu)
+    gr_nmf* padded = nullptr;    // handle of rank r4
+    float* d_wpad = nullptr;     // [n, r4]
+    float* d_hpad = nullptr;     // [r4, f]
 };
 
 namespace gr {

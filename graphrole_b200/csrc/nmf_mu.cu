@@ -331,6 +331,22 @@ nmf_error_tile_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int f
     }
 }
 
+// ---- rank padding: W [n, r] <-> [n, r4], zero columns from r on -----------------------------------
+__global__ void nmf_pad_w_kernel(const float* __restrict__ W, int64_t n, int r, int r4,
+                                 float* __restrict__ Wp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * r4) return;
+    const int64_t row = i / r4;
+    const int c = (int)(i % r4);
+    Wp[i] = c < r ? W[row * r + c] : 0.f;
+}
+__global__ void nmf_unpad_w_kernel(const float* __restrict__ Wp, int64_t n, int r, int r4,
+                                   float* __restrict__ W) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * r) return;
+    W[i] = Wp[(i / r) * r4 + i % r];
+}
+
 template <typename F>
 int dispatch_rp(int rp, F&& fn) {
     switch (rp) {
@@ -480,9 +496,56 @@ extern "C" int gr_nmf_create(gr_nmf_t** out, int64_t n, int32_t f, int32_t r, in
     return GR_OK;
 }
 
+// Zero-padded factors of rank r4 for the tensor-core kernels (r % 4 != 0).  A zero column of W and
+// the matching zero row of H are fixed points of the multiplicative updates (numerator 0,
+// denominator 0 -> eps, 0 * 0 / eps = 0) and add exact zeros to every sum the real roles see, so
+// the first r roles of the padded problem ARE the rank-r problem.
+static int ensure_padded(gr_nmf* h) {
+    if (h->padded) return GR_OK;
+    const int r4 = (h->r + 3) & ~3;
+    if (int rc = gr_nmf_create(&h->padded, h->n, h->f, r4, h->device)) return rc;
+    if (cudaMalloc(&h->d_wpad, (size_t)h->n * r4 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&h->d_hpad, (size_t)r4 * h->f * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GR_ERR_OUT_OF_MEMORY, "gr_nmf: padded factors (rank %d -> %d)", h->r, r4);
+    }
+    return GR_OK;
+}
+static int pad_factors(gr_nmf* h, const float* W, const float* H, cudaStream_t st) {
+    const int r4 = h->padded->r;
+    const int64_t cnt = h->n * r4;
+    nmf_pad_w_kernel<<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(W, h->n, h->r, r4,
+                                                                           h->d_wpad);
+    GR_LAUNCH_CHECK("nmf_pad_w_kernel");
+    GR_CUDA_TRY(cudaMemcpyAsync(h->d_hpad, H, (size_t)h->r * h->f * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    GR_CUDA_TRY(cudaMemsetAsync(h->d_hpad + (size_t)h->r * h->f, 0,
+                                (size_t)(r4 - h->r) * h->f * sizeof(float), st));
+    return GR_OK;
+}
+static int unpad_factors(gr_nmf* h, float* W, float* H, cudaStream_t st) {
+    const int64_t cnt = h->n * h->r;
+    nmf_unpad_w_kernel<<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(
+        h->d_wpad, h->n, h->r, h->padded->r, W);
+    GR_LAUNCH_CHECK("nmf_unpad_w_kernel");
+    GR_CUDA_TRY(cudaMemcpyAsync(H, h->d_hpad, (size_t)h->r * h->f * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    return GR_OK;
+}
+// true when the call should run on the padded handle (which then exists)
+static bool wants_padding(gr_nmf* h, const float* X, int64_t ldx, int* rc) {
+    *rc = GR_OK;
+    if (h->r % 4 == 0 || getenv("GR_NMF_NO_RANK_PADDING")) return false;
+    if ((*rc = ensure_padded(h)) != GR_OK) return false;
+    return nmf_tc_supported(h->padded, X, ldx);
+}
+
 extern "C" int gr_nmf_destroy(gr_nmf_t* h) {
     if (!h) return GR_OK;
     DeviceGuard guard(h->device);
+    if (h->padded) gr_nmf_destroy(h->padded);
+    cudaFree(h->d_wpad);
+    cudaFree(h->d_hpad);
     cudaFree(h->d_hht);
     cudaFree(h->d_wtw);
     cudaFree(h->d_h_next);
@@ -511,9 +574,18 @@ extern "C" int gr_nmf_error_tf32(gr_nmf_t* h, const float* X, int64_t ldx, const
     GR_REQUIRE(ldx >= h->f, "gr_nmf_error_tf32: ldx < f");
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    {
+        int rc;
+        if (wants_padding(h, X, ldx, &rc)) {
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            if ((rc = pad_factors(h, W, H, st)) != GR_OK) return rc;
+            return nmf_error_tc(h->padded, X, ldx, h->d_wpad, h->d_hpad, err_out, st);
+        }
+        if (rc) return rc;
+    }
     GR_REQUIRE(nmf_tc_supported(h, X, ldx),
-               "gr_nmf_error_tf32: shape not taken by the tensor-core kernels (r <= 32, r %% 4 == 0, "
-               "f %% 4 == 0, 16-byte aligned rows); use gr_nmf_error_f32");
+               "gr_nmf_error_tf32: shape not taken by the tensor-core kernels (r <= 32, f %% 4 == 0, "
+               "f <= 1024, 16-byte aligned rows); use gr_nmf_error_f32");
     return nmf_error_tc(h, X, ldx, W, H, err_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -527,6 +599,18 @@ extern "C" int gr_nmf_mu_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W,
     if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+    if (use_tf32) {      // r % 4 != 0: the same loop on zero-padded factors of rank r4
+        int rc;
+        if (wants_padding(h, X, ldx, &rc)) {
+            if ((rc = pad_factors(h, W, H, st)) != GR_OK) return rc;
+            rc = gr_nmf_mu_f32(h->padded, X, ldx, h->d_wpad, h->d_hpad, max_iter, tol,
+                               check_every, use_tf32, n_iter_out, err_out, stream);
+            h->last_path_tc = h->padded->last_path_tc;
+            if (rc) return rc;
+            return unpad_factors(h, W, H, st);
+        }
+        if (rc) return rc;
+    }
     const bool tc = use_tf32 && nmf_tc_supported(h, X, ldx);
     // the convergence checks follow the path of the iteration: W H on the tensor core beside the
     // tcgen05 iteration kernel (GR_NMF_ERROR_FFMA=1 keeps them on the fp32 FFMA pass)

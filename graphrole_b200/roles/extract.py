@@ -169,7 +169,7 @@ class DeviceModelGrid:
             if bool((V < 0).any()):
                 raise ValueError('Negative values in data passed to NMF')
             self.device = V.device
-            self.V = V.to(torch.float32).contiguous()
+            self._features = factor.FeatureMatrix(V)
         else:
             V = np.asarray(V)
             if V.ndim != 2:
@@ -179,8 +179,11 @@ class DeviceModelGrid:
             if np.any(V < 0):
                 raise ValueError('Negative values in data passed to NMF')
             self.device = device or _cuda_device()
-            self.V = torch.as_tensor(np.ascontiguousarray(V, dtype=np.float32),
-                                     device=self.device)
+            self._features = factor.FeatureMatrix(
+                torch.as_tensor(np.ascontiguousarray(V, dtype=np.float32), device=self.device))
+        # [n, f] view of a buffer whose rows are padded to a multiple of 4 columns, so that any
+        # feature count runs the tensor-core kernels
+        self.V = self._features.values
         self.n, self.f = self.V.shape
         self._factors: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._quantizers: Dict[int, Tuple[_native.Quantizer, _native.Quantizer]] = {}
@@ -196,7 +199,7 @@ class DeviceModelGrid:
                              f'{factor.MAX_ROLES}')
         if refit or n_roles not in self._factors:
             W0, H0 = factor.nndsvda_init(self.V, n_roles)
-            W, H, _, _ = factor.nmf_mu(self.V, W0, H0, max_iter=factor.MAX_ITER, tol=factor.TOL)
+            W, H, _, _ = self._features.nmf_mu(W0, H0, max_iter=factor.MAX_ITER, tol=factor.TOL)
             self.n_fits += 1
             self._drop_quantizers(n_roles)
             self._factors[n_roles] = (W, H)

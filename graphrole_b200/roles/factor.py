@@ -43,10 +43,39 @@ def get_nmf_decomposition(X: np.ndarray, n_roles: int) -> FactorTuple:
     if n_roles > MAX_ROLES:
         raise ValueError(f'n_roles = {n_roles}: the CUDA solver supports at most {MAX_ROLES}')
     device = torch.device('cuda', torch.cuda.current_device())
-    Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32), device=device)
-    W0, H0 = nndsvda_init(Xd, n_roles)
-    W, H, _, _ = nmf_mu(Xd, W0, H0, max_iter=MAX_ITER, tol=TOL)
+    Xd = FeatureMatrix(torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32), device=device))
+    W0, H0 = nndsvda_init(Xd.values, n_roles)
+    W, H, _, _ = Xd.nmf_mu(W0, H0, max_iter=MAX_ITER, tol=TOL)
     return W.double().cpu().numpy(), H.double().cpu().numpy()
+
+
+class FeatureMatrix:
+    """The float32 feature matrix in HBM, stored with its rows padded by zero columns to a
+    multiple of 4 features -- what the tensor-core kernels need (16-byte row pitch for TMA).
+    `values` is the [n, f] view, `padded` the [n, f4] buffer behind it.  A zero column of X is
+    inert in the factorisation: with the matching column of H0 set to zero it stays zero (its
+    update has numerator 0) and adds exact zeros to X H^T, H H^T and the residual, so the first
+    f columns of the padded problem are the problem."""
+
+    def __init__(self, V: torch.Tensor):
+        if not (isinstance(V, torch.Tensor) and V.is_cuda and V.dim() == 2):
+            raise ValueError('the feature matrix must be a 2-D CUDA tensor')
+        n, f = V.shape
+        f4 = -(-f // 4) * 4
+        if f4 == f:
+            self.padded = V.to(torch.float32).contiguous()
+        else:
+            self.padded = torch.zeros(n, f4, dtype=torch.float32, device=V.device)
+            self.padded[:, :f] = V
+        self.values = self.padded[:, :f]
+
+    def nmf_mu(self, W0: torch.Tensor, H0: torch.Tensor, **kwargs):
+        """nmf_mu on the padded matrix; returns (W, H [r, f], n_iter, error)."""
+        f, f4 = self.values.shape[1], self.padded.shape[1]
+        if f4 != f:
+            H0 = torch.nn.functional.pad(H0, (0, f4 - f))
+        W, H, n_iter, err = nmf_mu(self.padded, W0, H0, **kwargs)
+        return W, (H if f4 == f else H[:, :f].contiguous()), n_iter, err
 
 
 class NmfSolver:

@@ -203,8 +203,12 @@ int gr_nmf_mu_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                   int32_t max_iter, double tol, int32_t check_every, int32_t use_tf32,
                   int32_t* n_iter_out, double* err_out, void* stream);
 /* 1 when the last gr_nmf_mu_f32 call on this handle ran the tcgen05 kernel, 0 for the FFMA
- * kernels (use_tf32 == 0, or a shape the tensor-core kernel does not take: it needs r <= 32,
- * f % 4 == 0, f <= 1024, 16-byte aligned rows). */
+ * kernels (use_tf32 == 0, or a shape the tensor-core kernel does not take: it needs
+ * f % 4 == 0, f <= 1024, ldx % 4 == 0 and a 16-byte aligned X; a rank that is not a multiple of
+ * 4 runs there on zero-padded factors -- a zero role is a fixed point of the updates and adds
+ * exact zeros to every sum -- so that every n_roles of the reference's default grid, 2..8,
+ * takes the tensor-core path.  Feature counts that are not a multiple of 4: pad X with zero
+ * columns, as graphrole_b200.roles.extract.DeviceModelGrid does). */
 int gr_nmf_last_path(const gr_nmf_t* h);
 /* Frobenius error ||X - W H||_F (dense-residual form, _nmf.py:122), fp64 accumulation. */
 int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,

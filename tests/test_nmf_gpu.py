@@ -32,6 +32,17 @@ def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device='cuda:0')
 
 
+def run_mu(X, W0, H0, use_tf32, **kw):
+    """The multiplicative-update loop on the path under test.  TF32: through FeatureMatrix, like
+    the product (feature counts that are not a multiple of 4 are zero-padded), and the tcgen05
+    kernel must actually have run -- every golden case, whatever its rank and width."""
+    if not use_tf32:
+        return factor.nmf_mu(dev(X), dev(W0), dev(H0), use_tf32=False, **kw)
+    out = factor.FeatureMatrix(dev(X)).nmf_mu(dev(W0), dev(H0), use_tf32=True, **kw)
+    assert factor.last_path == 'tcgen05'
+    return out
+
+
 def rel_to_max(got, ref):
     return float(np.abs(got - ref).max() / np.abs(ref).max())
 
@@ -41,8 +52,7 @@ def rel_to_max(got, ref):
 def test_fixed_iterations_match_sklearn_golden(nmf_cases, name, r, use_tf32, tol_f, tol_e):
     z = nmf_cases
     X, W0, H0 = z[f'{name}__X'], z[f'{name}__r{r}__W0'], z[f'{name}__r{r}__H0']
-    W, H, n_iter, err = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=50, tol=0,
-                                      use_tf32=use_tf32)
+    W, H, n_iter, err = run_mu(X, W0, H0, use_tf32, max_iter=50, tol=0)
     assert n_iter == 50
     W, H = W.cpu().numpy().astype(np.float64), H.cpu().numpy().astype(np.float64)
     assert (W >= 0).all() and (H >= 0).all()
@@ -60,7 +70,7 @@ def test_convergence_loop_matches_sklearn(nmf_cases, name, r, use_tf32, tol_f):
     kernels and on the DEFAULT product path (tcgen05, TF32 contractions)."""
     z = nmf_cases
     X, W0, H0 = z[f'{name}__X'], z[f'{name}__r{r}__W0'], z[f'{name}__r{r}__H0']
-    W, H, n_iter, err = factor.nmf_mu(dev(X), dev(W0), dev(H0), use_tf32=use_tf32)
+    W, H, n_iter, err = run_mu(X, W0, H0, use_tf32)
     ref_iter = int(z[f'{name}__r{r}__n_iter'])
     assert abs(n_iter - ref_iter) <= 10 and n_iter % 10 == 0
     ref_err = float(z[f'{name}__r{r}__err'])
@@ -157,11 +167,14 @@ def test_error_pass_kernels_match_the_oracle(n, f, r, monkeypatch):
 def tf32_error_bound(want, W, H):
     """How far the TF32 rounding of the operands may move ||X - W H||_F.  Every term of W H is
     perturbed by <= 2^-11 relative and without bias: ||delta|| <= dn = 2^-11 ||W H||_F, and
-    ||d + delta|| - ||d|| ~ (d . delta) / ||d|| + ||delta||^2 / (2 ||d||) with d . delta a sum of
-    n f zero-mean terms.  1e-5 relative on top (fp32 residuals, accumulation order)."""
+    ||d + delta|| - ||d|| ~ (d . delta) / ||d|| + ||delta||^2 / (2 ||d||).  d . delta is a sum
+    of zero-mean terms of which r (n + f) are independent (one rounding per entry of W and of H:
+    the error of one entry of H moves a whole column of W H the same way).  1e-5 relative on top
+    (fp32 residuals, accumulation order)."""
     W, H = np.asarray(W, dtype=np.float64), np.asarray(H, dtype=np.float64)
     dn = 2.0 ** -11 * np.linalg.norm(W @ H)
-    return 1e-5 * want + 3 * dn / np.sqrt(W.shape[0] * H.shape[1]) + dn * dn / (2 * want)
+    independent = W.shape[1] * (W.shape[0] + H.shape[1])
+    return 1e-5 * want + 3 * dn / np.sqrt(independent) + dn * dn / (2 * want)
 
 
 @pytest.mark.parametrize('n,f,r', [(1, 4, 4), (127, 32, 4), (129, 36, 8), (257, 512, 32),
@@ -194,7 +207,9 @@ def test_tensor_core_error_pass_matches_the_oracle(n, f, r):
     assert abs(got - want) <= tf32_error_bound(want, Wn, Hn)
     if n * f >= 100_000:
         assert got == pytest.approx(want, rel=2e-5)
-    assert factor.nmf_error(dev(X32), Wd, Hd) == pytest.approx(want, rel=1e-5)
+    # (the fp32 FFMA pass: on an exact fit all that is left of the residual is fp32 rounding)
+    assert factor.nmf_error(dev(X32), Wd, Hd) == pytest.approx(
+        want, rel=1e-5, abs=1e-6 * np.linalg.norm(X32))
 
 
 def test_tensor_core_error_pass_refuses_other_shapes():
@@ -246,14 +261,18 @@ def test_config5_10m_x_512_at_size():
 
 
 def test_tensor_core_path_is_taken_and_matches_ffma():
-    """Shapes the tcgen05 kernel takes (r % 4 == 0, f % 4 == 0, f <= 1024) must actually run it --
-    no silent fallback -- and agree with the FFMA kernels; other shapes report 'ffma'."""
+    """Shapes the tcgen05 kernel takes (f % 4 == 0, f <= 1024; any rank up to 32 -- ranks that are
+    not a multiple of 4 run on zero-padded factors inside the library) must actually run it -- no
+    silent fallback -- and agree with the FFMA kernels; other shapes report 'ffma'."""
     rng = np.random.RandomState(3)
     for n, f, r, expect in [(3000, 512, 32, 'tcgen05'), (64 * 148 * 2 + 5, 128, 8, 'tcgen05'),
                             (1000, 96, 12, 'tcgen05'), (500, 704, 16, 'tcgen05'),
                             (500, 768, 16, 'tcgen05'), (9000, 1024, 32, 'tcgen05'),
                             (700, 132, 4, 'tcgen05'), (64 * 74 * 3 + 1, 256, 32, 'tcgen05'),
-                            (500, 1028, 16, 'ffma'), (500, 64, 5, 'ffma'), (500, 30, 4, 'ffma')]:
+                            (500, 64, 5, 'tcgen05'), (400, 128, 2, 'tcgen05'),
+                            (400, 96, 7, 'tcgen05'), (64 * 148 + 3, 512, 29, 'tcgen05'),
+                            (257, 36, 3, 'tcgen05'), (200, 8, 1, 'tcgen05'),
+                            (500, 1028, 16, 'ffma'), (500, 30, 4, 'ffma')]:
         X = rng.rand(n, f)
         W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
         Wt, Ht, _, _ = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=5, tol=0, use_tf32=True)
@@ -262,6 +281,29 @@ def test_tensor_core_path_is_taken_and_matches_ffma():
         assert factor.last_path == 'ffma'
         assert rel_to_max(Wt.cpu().numpy(), Wf.cpu().numpy()) < 5e-3
         assert rel_to_max(Ht.cpu().numpy(), Hf.cpu().numpy()) < 5e-3
+
+
+@pytest.mark.parametrize('n,f,r', [(600, 30, 5), (300, 7, 3), (1000, 513, 6), (64, 33, 2)])
+def test_any_feature_count_runs_the_tensor_core_path(n, f, r):
+    """factor.FeatureMatrix stores the features with zero columns up to a multiple of 4 (the
+    16-byte row pitch TMA needs): the padded problem's first f columns are the problem -- same
+    factors as the unpadded FFMA run to the TF32 tolerance, H's padding stays exactly zero, same
+    error as the unpadded matrix."""
+    rng = np.random.RandomState(f)
+    X = rng.rand(n, f)
+    W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+    fm = factor.FeatureMatrix(dev(X))
+    assert fm.padded.shape[1] % 4 == 0 and fm.values.shape == (n, f)
+    assert bool((fm.padded[:, f:] == 0).all()) and bool((fm.values == dev(X)).all())
+    Wt, Ht, it_t, err_t = fm.nmf_mu(dev(W0), dev(H0), max_iter=20, tol=0)
+    assert factor.last_path == 'tcgen05' and Ht.shape == (r, f) and it_t == 20
+    Wf, Hf, _, err_f = factor.nmf_mu(dev(X), dev(W0), dev(H0), max_iter=20, tol=0, use_tf32=False)
+    assert factor.last_path == 'ffma'
+    assert rel_to_max(Wt.cpu().numpy(), Wf.cpu().numpy()) < 1e-2
+    assert rel_to_max(Ht.cpu().numpy(), Hf.cpu().numpy()) < 1e-2
+    assert err_t == pytest.approx(err_f, rel=1e-3)
+    assert err_t == pytest.approx(
+        oracle.frobenius_error(X, Wt.double().cpu().numpy(), Ht.double().cpu().numpy()), rel=1e-4)
 
 
 def test_zero_denominators_and_edge_shapes():

@@ -82,8 +82,8 @@ def main():
                 'launches_per_iter': launches / iters, 'ms_per_check': round(ms_check, 3),
                 'ms_per_iter_with_checks': round(ms_checked, 3), 'iters_with_checks': n_it,
                 'error_at_check': err_c,
-                'error_pass': 'ffma' if os.environ.get('GR_NMF_ERROR_FFMA') or not use_tf32
-                else 'tcgen05'}), flush=True)
+                'error_pass': 'ffma' if os.environ.get('GR_NMF_ERROR_FFMA') or
+                solver.last_path != 'tcgen05' else 'tcgen05'}), flush=True)
             solver.close()
             del W, H
         del W0, H0
