@@ -679,12 +679,14 @@ def next_rows_section(g, d, device):
     return out
 
 
-def nmf_section(device, n=10_000_000, f=512, ranks=(4, 8, 16, 32), iters=10):
+def nmf_section(device, n=10_000_000, f=512, ranks=(2, 4, 5, 8, 16, 32), iters=10):
     """Hot path B on C5 (X = 10M x 512 fp32, synthetic U[0,1)), tcgen05 path:
     * ms per multiplicative-update iteration with tol = 0 (no convergence pass in the timed
       region); algorithmic bytes n*f*4 + 2*n*r*4;
     * the same with sklearn's defaults (tol = 1e-4, dense-residual check every 10 iterations):
-      what get_nmf_decomposition actually runs;
+      what get_nmf_decomposition actually runs (the checks run W H on tcgen05 as well), and one
+      check alone; ranks 2 and 5 stand for the n_roles of the reference's default grid (2..8) that
+      are not a multiple of 4: the library runs them on zero-padded factors;
     * the RolX epilogue at this size: quantiser, description-length cost and the whole
       (n_roles, n_bits) model-selection grid on device-resident factors."""
     from graphrole_b200 import _native
@@ -711,13 +713,19 @@ def nmf_section(device, n=10_000_000, f=512, ranks=(4, 8, 16, 32), iters=10):
         e1.record()
         torch.cuda.synchronize()
         ms_checked = e0.elapsed_time(e1) / max(n_it, 1)
+        e0.record()
+        solver.update(X, W, H, max_iter=0, tol=1e-30)      # the error at init alone = one check
+        e1.record()
+        torch.cuda.synchronize()
+        ms_check = e0.elapsed_time(e1)
         alg = n * f * 4 + 2 * n * r * 4
         flops = 4 * n * f * r + 4 * n * r * r + 2 * r * r * f
         rows.append({'r': r, 'path': solver.last_path, 'ms_per_iter': ms,
                      'alg_GBps': alg / ms / 1e6, 'frac_of_hbm_peak': alg / ms / 1e6 / peak,
                      'alg_TFLOPs': flops / ms / 1e9,
                      'ms_per_iter_with_convergence_checks': ms_checked,
-                     'iterations_with_checks': n_it})
+                     'iterations_with_checks': n_it, 'ms_per_convergence_check': ms_check,
+                     'check_GBps_of_X': n * f * 4 / ms_check / 1e6})
         solver.close()
         del W, H
     out = {'workload': f'X {n}x{f} fp32 U[0,1), shared random init, {iters} iterations',
@@ -782,6 +790,7 @@ def rolx_epilogue_section(X, device, n_roles=8):
     # the grid, on a planted low-rank matrix so that the fits converge like real features do
     t0 = time.perf_counter()
     grid = DeviceModelGrid.from_device(X)
+    grid.timed = True
     cells = 0
     for roles in (2, 4, 8):
         for bits in range(1, 9):
@@ -789,7 +798,9 @@ def rolx_epilogue_section(X, device, n_roles=8):
             cells += 1
     torch.cuda.synchronize()
     out['model_selection_grid'] = {'cells': cells, 'n_roles': [2, 4, 8], 'n_bits': [1, 8],
-                                   'nmf_fits': grid.n_fits, 'wall_s': time.perf_counter() - t0}
+                                   'nmf_fits': grid.n_fits, 'wall_s': time.perf_counter() - t0,
+                                   'phase_s': {k: round(v, 3) for k, v in grid.timings_s.items()},
+                                   'nmf_iterations': dict(grid.nmf_iterations)}
     grid.close()
     return out
 

@@ -188,6 +188,22 @@ class DeviceModelGrid:
         self._factors: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._quantizers: Dict[int, Tuple[_native.Quantizer, _native.Quantizer]] = {}
         self.n_fits = 0
+        # set `timed` before the first call to get seconds per phase in `timings_s` (every phase
+        # is then bracketed by a device synchronisation)
+        self.timed = False
+        self.timings_s: Dict[str, float] = {}
+        self.nmf_iterations: Dict[int, int] = {}
+
+    def _phase(self, name: str, fn):
+        if not self.timed:
+            return fn()
+        import time
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize(self.device)
+        self.timings_s[name] = self.timings_s.get(name, 0.0) + time.perf_counter() - t0
+        return out
 
     @classmethod
     def from_device(cls, V: torch.Tensor) -> 'DeviceModelGrid':
@@ -198,8 +214,10 @@ class DeviceModelGrid:
             raise ValueError(f'n_roles = {n_roles}: the CUDA solver supports at most '
                              f'{factor.MAX_ROLES}')
         if refit or n_roles not in self._factors:
-            W0, H0 = factor.nndsvda_init(self.V, n_roles)
-            W, H, _, _ = self._features.nmf_mu(W0, H0, max_iter=factor.MAX_ITER, tol=factor.TOL)
+            W0, H0 = self._phase('nndsvda_init', lambda: factor.nndsvda_init(self.V, n_roles))
+            W, H, n_iter, _ = self._phase('nmf_mu', lambda: self._features.nmf_mu(
+                W0, H0, max_iter=factor.MAX_ITER, tol=factor.TOL))
+            self.nmf_iterations[n_roles] = n_iter
             self.n_fits += 1
             self._drop_quantizers(n_roles)
             self._factors[n_roles] = (W, H)
@@ -212,23 +230,24 @@ class DeviceModelGrid:
     def quantizers(self, n_roles: int, refit: bool = False):
         W, H = self.factors(n_roles, refit)
         if n_roles not in self._quantizers:
-            self._quantizers[n_roles] = (_native.Quantizer(W.numel(), self.device).bind(W),
-                                         _native.Quantizer(H.numel(), self.device).bind(H))
+            self._quantizers[n_roles] = self._phase('quantizer_bind', lambda: (
+                _native.Quantizer(W.numel(), self.device).bind(W),
+                _native.Quantizer(H.numel(), self.device).bind(H)))
         return self._quantizers[n_roles]
 
     def encoded(self, n_roles: int, n_bits: int, refit: bool = False):
         """(G_encoded, F_encoded, codebook size of G, of F) on the device."""
         n_bins = int(2 ** n_bits)
         qG, qF = self.quantizers(n_roles, refit)
-        G, info_g = qG.encode(n_bins)
-        F, info_f = qF.encode(n_bins)
+        G, info_g = self._phase('encode', lambda: qG.encode(n_bins))
+        F, info_f = self._phase('encode', lambda: qF.encode(n_bins))
         return G, F, info_g['n_distinct'], info_f['n_distinct']
 
     def costs(self, n_roles: int, n_bits: int, refit: bool = False) -> Tuple[float, float]:
         """(encoding cost, error cost) of one grid cell (description_length.py:8-29)."""
         G, F, n_g, n_f = self.encoded(n_roles, n_bits, refit)
         return (encoding_cost_from_counts(n_g, n_f, G.numel() + F.numel()),
-                _native.mdl_error_cost(self.V, G, F))
+                self._phase('error_cost', lambda: _native.mdl_error_cost(self.V, G, F)))
 
     def model(self, n_roles: int, n_bits: int) -> FactorTuple:
         """The cell's encoded factors as float64 host arrays (what the reference returns)."""

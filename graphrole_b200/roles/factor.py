@@ -184,6 +184,35 @@ def nmf_error(X: torch.Tensor, W: torch.Tensor, H: torch.Tensor, use_tf32: bool 
     return float(err.value)
 
 
+def orthonormal_basis(Y: torch.Tensor) -> torch.Tensor:
+    """Orthonormal basis of range(Y), Y [m, k] -- the `Q` of sklearn's range finder
+    (sklearn/utils/extmath.py randomized_range_finder: linalg.qr(A @ Q, mode='economic')).
+
+    Tall matrices (m >= 64 k: the n x k sketches of a feature matrix) take CholeskyQR2 with a
+    float64 Gram matrix: two passes of [G = Y^T Y, Y <- Y chol(G)^-T], i.e. four streaming reads
+    of Y instead of k Householder reflections over it (cuSOLVER's geqrf + orgqr took ~0.15 s per
+    10 M x 18 sketch, 8 sketches per init: 1.65 s of a C5 initialisation, against 0.9 s for the
+    whole multiplicative-update fit).  Any orthonormal basis of the same range gives the same
+    projection B = Q^T A, hence the same U, S, V.  The Gram matrix squares the condition number,
+    so the float64 Cholesky fails beyond cond(Y) ~ 1e8 (an exactly rank-deficient sketch, e.g.
+    rank(X) < k); then -- and for short matrices -- Householder QR as before."""
+    m, k = Y.shape
+    if m < 64 * k:
+        return torch.linalg.qr(Y)[0]
+    Q = Y.double()
+    for _ in range(2):
+        G = Q.T @ Q
+        L, info = torch.linalg.cholesky_ex(G)
+        if int(info) != 0 or not bool(torch.isfinite(L).all()):
+            return torch.linalg.qr(Y)[0]
+        Q = Q @ torch.linalg.inv(L).T
+    # a sketch whose Cholesky factor went through but lost the basis (cond^2 near 1 / eps)
+    dev = (Q.T @ Q - torch.eye(k, dtype=Q.dtype, device=Q.device)).abs().max()
+    if not bool(dev < 1e-6):
+        return torch.linalg.qr(Y)[0]
+    return Q.to(Y.dtype)
+
+
 def nndsvda_init(X: torch.Tensor, n_components: int, eps: float = 1e-6,
                  n_oversamples: int = 10,
                  seed: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -203,10 +232,10 @@ def nndsvda_init(X: torch.Tensor, n_components: int, eps: float = 1e-6,
     work = torch.float64 if n * f <= (1 << 26) else torch.float32
     A = X.to(work)
     Q = torch.from_numpy(rng.normal(size=(f, k))).to(X.device, work)
-    Q, _ = torch.linalg.qr(A @ Q)
+    Q = orthonormal_basis(A @ Q)
     for _ in range(n_iter):
-        Q, _ = torch.linalg.qr(A.T @ Q)
-        Q, _ = torch.linalg.qr(A @ Q)
+        Q = orthonormal_basis(A.T @ Q)
+        Q = orthonormal_basis(A @ Q)
     B = Q.T @ A                                   # k x f
     Ub, S, Vt = torch.linalg.svd(B.double(), full_matrices=False)
     U = (Q.double() @ Ub)[:, :n_components]

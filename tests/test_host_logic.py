@@ -343,3 +343,33 @@ def test_rescale_costs_and_role_extractor_surface():
                                        columns=['role_0', 'role_1'])
     assert rx.roles == {'x': 'role_1', 'y': 'role_0'}
     np.testing.assert_allclose(rx.role_percentage.values, [[0.25, 0.75], [0.5, 0.5]])
+
+
+def test_orthonormal_basis_cholesky_qr2_and_householder_fallback():
+    """The range finder's basis (factor.orthonormal_basis): CholeskyQR2 for tall sketches gives an
+    orthonormal basis of the same range as Householder QR; a rank-deficient sketch (the float64
+    Cholesky fails) and a short one take Householder QR itself."""
+    import torch
+    gen = torch.Generator().manual_seed(0)
+    for m, k, cond, via_cholesky in [(20000, 18, 1e2, True), (20000, 12, 1e4, True),
+                                     (20000, 12, 1e12, False), (100, 18, 10, False)]:
+        U, _ = torch.linalg.qr(torch.randn(m, k, dtype=torch.float64, generator=gen))
+        V, _ = torch.linalg.qr(torch.randn(k, k, dtype=torch.float64, generator=gen))
+        sv = torch.logspace(0, -np.log10(cond), k, dtype=torch.float64)
+        Y = ((U * sv) @ V.T).float()
+        Q = factor.orthonormal_basis(Y)
+        assert Q.shape == (m, k) and Q.dtype == Y.dtype
+        Qd = Q.double()
+        assert float((Qd.T @ Qd - torch.eye(k, dtype=torch.float64)).abs().max()) < 1e-6
+        Qh = torch.linalg.qr(Y)[0]
+        if not via_cholesky:
+            assert torch.equal(Q, Qh)
+        elif cond <= 1e2:           # every direction resolved in float32: same range
+            assert float((Qd @ (Qd.T @ Qh.double()) - Qh.double()).abs().max()) < 1e-4
+    # 18 columns of rank 5 (up to float32 rounding): whichever route it takes, the basis is
+    # orthonormal and holds the 5-dimensional range
+    A5 = torch.randn(5000, 5, generator=gen)
+    Q = factor.orthonormal_basis(A5 @ torch.randn(5, 18, generator=gen)).double()
+    assert float((Q.T @ Q - torch.eye(18, dtype=torch.float64)).abs().max()) < 1e-6
+    B5 = torch.linalg.qr(A5.double())[0]
+    assert float((Q @ (Q.T @ B5) - B5).abs().max()) < 1e-4

@@ -365,6 +365,30 @@ def test_nndsvda_init_matches_sklearn_on_separated_spectrum():
     np.testing.assert_allclose(H.cpu().numpy(), H_ref, rtol=2e-4, atol=1e-5)
 
 
+def test_nndsvda_init_tall_matrix_same_start_as_householder_qr(monkeypatch):
+    """The sketches of a tall feature matrix are orthonormalised by CholeskyQR2
+    (factor.orthonormal_basis); the start it leads to equals the one from Householder QR -- any
+    orthonormal basis of the same range gives the same projection -- and sklearn's."""
+    sk = pytest.importorskip('sklearn.decomposition._nmf')
+    rng = np.random.RandomState(1)
+    X = (rng.rand(6000, 5) ** 2 * np.array([9.0, 5.0, 3.0, 2.0, 1.0])) @ rng.rand(5, 40) + \
+        0.01 * rng.rand(6000, 40)
+    np.random.seed(7)
+    W, H = factor.nndsvda_init(dev(X), 4)
+    calls = []
+    real_qr = torch.linalg.qr
+    monkeypatch.setattr(factor, 'orthonormal_basis', lambda Y: (calls.append(1), real_qr(Y)[0])[1])
+    np.random.seed(7)
+    Wh, Hh = factor.nndsvda_init(dev(X), 4)
+    assert calls
+    np.testing.assert_allclose(W.cpu().numpy(), Wh.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(H.cpu().numpy(), Hh.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.random.seed(7)
+    W_ref, H_ref = sk._initialize_nmf(X, 4, init='nndsvda')
+    np.testing.assert_allclose(W.cpu().numpy(), W_ref, rtol=5e-4, atol=2e-5)
+    np.testing.assert_allclose(H.cpu().numpy(), H_ref, rtol=5e-4, atol=2e-5)
+
+
 def test_role_extractor_end_to_end(refex_cases):
     """RoleExtractor surface on the karate features (tests/test_roles/test_extract.py:38-75)."""
     from helpers import frame_from_json
