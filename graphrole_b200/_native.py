@@ -56,6 +56,7 @@ SIGNATURES = {
     'gr_nmf_mu_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_double,
                               c_int32, c_int32, POINTER(c_int32), POINTER(c_double), c_void_p]),
     'gr_nmf_last_path': (c_int, [c_void_p]),
+    'gr_nmf_takes_tensor_cores': (c_int, [c_void_p, c_void_p, c_int64]),
     'gr_pruner_create': (c_int, [POINTER(c_void_p), c_int64, c_int]),
     'gr_pruner_destroy': (c_int, [c_void_p]),
     'gr_prune_bin_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p,
@@ -71,6 +72,9 @@ SIGNATURES = {
                                  POINTER(c_double), c_void_p]),
     'gr_nmf_error_tf32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                   POINTER(c_double), c_void_p]),
+    'gr_nmf_iteration_local_f32': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32,
+                                           c_void_p, c_void_p, c_void_p]),
+    'gr_nmf_update_h_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'gr_quantizer_create': (c_int, [POINTER(c_void_p), c_int64, c_int]),
     'gr_quantizer_destroy': (c_int, [c_void_p]),
     'gr_quantizer_bind_f32': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

@@ -24,6 +24,12 @@ struct gr_nmf {
     void* tc_state = nullptr;    // owned by nmf_mu_tc.cu
     // r % 4 != 0 on the tensor-core path: rows of W [n, r] are not 16-byte multiples (TMA), so
     // the loop runs on zero-padded factors of rank r4 = r rounded up to 4 (nmf_mu.cu)
+    // row-sharded runs (gr_nmf_iteration_local_f32): stop an iteration before the reduction of
+    // the partial sums and remember where they are
+    bool defer_finish = false;
+    const float* pending_wtx = nullptr;
+    const float* pending_wtw = nullptr;
+    int pending_splits = 0, pending_rp = 0;
     gr_nmf* padded = nullptr;    // handle of rank r4
     float* d_wpad = nullptr;     // [n, r4]
     float* d_hpad = nullptr;     // [r4, f]

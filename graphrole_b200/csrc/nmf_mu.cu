@@ -163,6 +163,18 @@ nmf_reduce_wtw_kernel(const float* __restrict__ part, int splits, int rp, int r,
     WtW[i * r + j] = acc;
 }
 
+// ---- fixed-order reduction of the W^T X partials (r x f): grid (column slabs, r) ---------------
+__global__ void __launch_bounds__(kThreads)
+nmf_reduce_wtx_kernel(const float* __restrict__ part, int splits, int rp, int f,
+                      float* __restrict__ WtX) {
+    const int col = blockIdx.x * kThreads + threadIdx.x;
+    const int l = blockIdx.y;
+    if (col >= f) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * rp + l) * f + col];
+    WtX[(int64_t)l * f + col] = acc;
+}
+
 // ---- H update: reduce W^T X partials, H_next = H * WtX / (WtW H) --------------------------------
 // One thread per (role, column): grid (column slabs, r).  Reads the old H, writes H_next (the
 // caller copies it back), so no thread sees a half-updated column.
@@ -400,6 +412,13 @@ int gr::nmf_iteration_fma(gr_nmf* h, const float* X, int64_t ldx, float* W, floa
 // Shared tail of an iteration: reduce the partials, update H.
 int gr::nmf_finish_iteration(gr_nmf* h, const float* part_wtx, const float* part_wtw, int splits,
                              int rp, float* H, cudaStream_t st) {
+    if (h->defer_finish) {      // row-sharded: the sums still have to cross the ranks
+        h->pending_wtx = part_wtx;
+        h->pending_wtw = part_wtw;
+        h->pending_splits = splits;
+        h->pending_rp = rp;
+        return GR_OK;
+    }
     nmf_reduce_wtw_kernel<<<1, 1024, 0, st>>>(part_wtw, splits, rp, h->r, h->d_wtw);
     GR_LAUNCH_CHECK("nmf_reduce_wtw_kernel");
     dim3 grid((unsigned)ceil_div(h->f, kThreads), (unsigned)h->r);
@@ -559,6 +578,18 @@ extern "C" int gr_nmf_destroy(gr_nmf_t* h) {
 
 extern "C" int gr_nmf_last_path(const gr_nmf_t* h) { return h && h->last_path_tc ? 1 : 0; }
 
+extern "C" int gr_nmf_takes_tensor_cores(const gr_nmf_t* h, const float* X, int64_t ldx) {
+    if (!h || !X) return 0;
+    if (nmf_tc_supported(h, X, ldx)) return 1;
+    if (h->r % 4 == 0 || getenv("GR_NMF_NO_RANK_PADDING")) return 0;
+    gr_nmf probe;               // the shape the padded run would have
+    probe.n = h->n;
+    probe.f = h->f;
+    probe.r = (h->r + 3) & ~3;
+    probe.device = h->device;
+    return nmf_tc_supported(&probe, X, ldx) ? 1 : 0;
+}
+
 extern "C" int gr_nmf_error_f32(gr_nmf_t* h, const float* X, int64_t ldx, const float* W,
                                 const float* H, double* err_out, void* stream) {
     GR_REQUIRE(h && X && W && H && err_out, "gr_nmf_error_f32: NULL argument");
@@ -587,6 +618,47 @@ extern "C" int gr_nmf_error_tf32(gr_nmf_t* h, const float* X, int64_t ldx, const
                "gr_nmf_error_tf32: shape not taken by the tensor-core kernels (r <= 32, f %% 4 == 0, "
                "f <= 1024, 16-byte aligned rows); use gr_nmf_error_f32");
     return nmf_error_tc(h, X, ldx, W, H, err_out, static_cast<cudaStream_t>(stream));
+}
+
+// ---- row-sharded form (path B): one iteration cut at the reduction ------
+extern "C" int gr_nmf_iteration_local_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W,
+                                          const float* H, int32_t use_tf32, float* wtx_out,
+                                          float* wtw_out, void* stream) {
+    GR_REQUIRE(h && X && W && H && wtx_out && wtw_out, "gr_nmf_iteration_local_f32: NULL argument");
+    GR_REQUIRE(ldx >= h->f, "gr_nmf_iteration_local_f32: ldx < f");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool tc = use_tf32 && nmf_tc_supported(h, X, ldx);
+    h->defer_finish = true;
+    // neither path writes H before nmf_finish_iteration, which is deferred here
+    const int rc = tc ? nmf_iteration_tc(h, X, ldx, W, const_cast<float*>(H), st)
+                      : nmf_iteration_fma(h, X, ldx, W, const_cast<float*>(H), st);
+    h->defer_finish = false;
+    h->last_path_tc = tc;
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(h->f, kThreads), (unsigned)h->r);
+    nmf_reduce_wtx_kernel<<<grid, kThreads, 0, st>>>(h->pending_wtx, h->pending_splits,
+                                                    h->pending_rp, h->f, wtx_out);
+    GR_LAUNCH_CHECK("nmf_reduce_wtx_kernel");
+    nmf_reduce_wtw_kernel<<<1, 1024, 0, st>>>(h->pending_wtw, h->pending_splits, h->pending_rp,
+                                              h->r, wtw_out);
+    GR_LAUNCH_CHECK("nmf_reduce_wtw_kernel");
+    return GR_OK;
+}
+
+extern "C" int gr_nmf_update_h_f32(gr_nmf_t* h, const float* wtx, const float* wtw, float* H,
+                                   void* stream) {
+    GR_REQUIRE(h && wtx && wtw && H, "gr_nmf_update_h_f32: NULL argument");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(GR_ERR_CUDA, "cannot select device %d", h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)ceil_div(h->f, kThreads), (unsigned)h->r);
+    nmf_update_h_kernel<<<grid, kThreads, 0, st>>>(wtx, 1, h->r, h->r, h->f, wtw, H, h->d_h_next);
+    GR_LAUNCH_CHECK("nmf_update_h_kernel");
+    GR_CUDA_TRY(cudaMemcpyAsync(H, h->d_h_next, (size_t)h->r * h->f * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    return GR_OK;
 }
 
 extern "C" int gr_nmf_mu_f32(gr_nmf_t* h, const float* X, int64_t ldx, float* W, float* H,

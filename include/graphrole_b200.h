@@ -210,6 +210,8 @@ int gr_nmf_mu_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
  * takes the tensor-core path.  Feature counts that are not a multiple of 4: pad X with zero
  * columns, as graphrole_b200.roles.extract.DeviceModelGrid does). */
 int gr_nmf_last_path(const gr_nmf_t* h);
+/* 1 when gr_nmf_mu_f32(use_tf32 != 0) on this X would run the tcgen05 kernels, else 0. */
+int gr_nmf_takes_tensor_cores(const gr_nmf_t* h, const float* X_dev, int64_t ldx);
 /* Frobenius error ||X - W H||_F (dense-residual form, _nmf.py:122), fp64 accumulation. */
 int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                      const float* W_dev, const float* H_dev, double* err_out, void* stream);
@@ -219,6 +221,22 @@ int gr_nmf_error_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
  * kernels do not take (see gr_nmf_last_path). */
 int gr_nmf_error_tf32(gr_nmf_t* h, const float* X_dev, int64_t ldx,
                       const float* W_dev, const float* H_dev, double* err_out, void* stream);
+
+/* Row-sharded form of path B: rows of X and W are split over the ranks, H
+ * is replicated.  One multiplicative-update iteration is cut where the sums cross the ranks:
+ *   gr_nmf_iteration_local_f32   W update of the local rows (in place) and the local sums
+ *                                wtx_out [r, f] = W^T X, wtw_out [r, r] = W^T W (device buffers,
+ *                                updated W); H is read only
+ *   (caller: all-reduce(sum) of wtx / wtw over the ranks -- NCCL; r f + r^2 floats)
+ *   gr_nmf_update_h_f32          H *= wtx / (wtw H) in place (_nmf.py:633-635, 701-721); identical
+ *                                on every rank because its inputs are
+ * Convergence: gr_nmf_error_tf32 / _f32 give the local ||X - W H||_F; the caller sums the
+ * squares over the ranks.  Host loop: graphrole_b200/roles/sharded.py::RowShardedNmf. */
+int gr_nmf_iteration_local_f32(gr_nmf_t* h, const float* X_dev, int64_t ldx, float* W_dev,
+                               const float* H_dev, int32_t use_tf32, float* wtx_out_dev,
+                               float* wtw_out_dev, void* stream);
+int gr_nmf_update_h_f32(gr_nmf_t* h, const float* wtx_dev, const float* wtw_dev, float* H_dev,
+                        void* stream);
 
 /* ---- "next" rows of the path: what runs between the levels -------------
  *

@@ -306,6 +306,76 @@ def test_any_feature_count_runs_the_tensor_core_path(n, f, r):
         oracle.frobenius_error(X, Wt.double().cpu().numpy(), Ht.double().cpu().numpy()), rel=1e-4)
 
 
+def test_row_sharded_loop_on_one_rank_is_the_library_loop():
+    """roles/sharded.py::RowShardedNmf with a single shard (no process group): the split
+    iteration (gr_nmf_iteration_local_f32 + gr_nmf_update_h_f32) adds the per-CTA partials in the
+    same order as gr_nmf_mu_f32, so factors, stopping iteration and error are bit-identical --
+    on the tcgen05 path and on the FFMA path, padded ranks included."""
+    from graphrole_b200.roles.sharded import nmf_mu_row_sharded
+    rng = np.random.RandomState(11)
+    for n, f, r, use_tf32 in [(64 * 148 + 77, 512, 8, True), (3000, 96, 5, True),
+                              (2000, 70, 6, False)]:
+        X = (rng.rand(n, 6) ** 2) @ rng.rand(6, f) + 0.05 * rng.rand(n, f)
+        W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+        Ws, Hs, it_s, err_s = nmf_mu_row_sharded(dev(X), dev(W0), dev(H0), use_tf32=use_tf32)
+        Wl, Hl, it_l, err_l = factor.nmf_mu(dev(X), dev(W0), dev(H0), use_tf32=use_tf32)
+        assert factor.last_path == ('tcgen05' if use_tf32 else 'ffma')
+        assert it_s == it_l and err_s == err_l
+        assert torch.equal(Ws, Wl) and torch.equal(Hs, Hl)
+
+
+@pytest.mark.parametrize('shards', [2, 3])
+def test_row_sharded_iterations_match_unsharded(shards):
+    """The exchange step emulated on one GPU: every shard runs gr_nmf_iteration_local_f32 on its
+    rows, the [W^T X | W^T W] sums are added (what the all-reduce does) and every shard applies
+    gr_nmf_update_h_f32 -- every shard holds the same H bit for bit, and the factors equal the
+    unsharded run up to the order of the fp32 partial sums.  On the tcgen05 path W is held at TF32
+    precision, so a last-bit difference in H can flip the rounding of an entry of W by one TF32
+    step (2^-11 of its value): stated 4e-3 of the largest entry for W, 5e-4 for H after 20
+    iterations (measured 1.7e-3 / < 1e-4).  The real two-GPU run: test_two_gpu_row_sharded_nmf."""
+    from graphrole_b200.roles.sharded import CudaNmfBackend, row_shard
+    rng = np.random.RandomState(shards)
+    n, f, r = 128 * 40 + 19, 256, 8
+    X = (rng.rand(n, 6) ** 2) @ rng.rand(6, f) + 0.05 * rng.rand(n, f)
+    W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+    Xd = dev(X)
+    spans = [row_shard(n, shards, s) for s in range(shards)]
+    Ws = [dev(W0[lo:hi]) for lo, hi in spans]
+    Hs = [dev(H0) for _ in spans]
+    backends = [CudaNmfBackend(hi - lo, f, r, Xd.device) for lo, hi in spans]
+    for _ in range(20):
+        sums = [b.local_iteration(Xd[lo:hi], W, H).clone()
+                for b, (lo, hi), W, H in zip(backends, spans, Ws, Hs)]
+        total = torch.stack(sums).sum(dim=0)
+        for b, H in zip(backends, Hs):
+            b.update_h(total, H)
+    assert all(b.last_path == 'tcgen05' for b in backends)
+    err_sq = sum(b.error_sq(Xd[lo:hi], W, H) for b, (lo, hi), W, H in zip(backends, spans, Ws, Hs))
+    for b in backends:
+        b.close()
+    Wu, Hu, _, err_u = factor.nmf_mu(Xd, dev(W0), dev(H0), max_iter=20, tol=0)
+    for H in Hs[1:]:
+        assert torch.equal(H, Hs[0])
+    assert rel_to_max(torch.cat(Ws).cpu().numpy(), Wu.cpu().numpy()) < 4e-3
+    assert rel_to_max(Hs[0].cpu().numpy(), Hu.cpu().numpy()) < 5e-4
+    assert err_sq ** 0.5 == pytest.approx(err_u, rel=1e-5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one box')
+def test_two_gpu_row_sharded_nmf():
+    """torchrun, one rank per GPU, NCCL all-reduce (tools/check_sharded_nmf.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', '29741',
+         os.path.join(root, 'tools', 'check_sharded_nmf.py'), '--n', '300000'],
+        capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'SHARDED NMF CHECK OK' in res.stdout, res.stdout + res.stderr
+
+
 def test_zero_denominators_and_edge_shapes():
     X = np.array([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 0.0]])
     W0 = np.array([[1.0, 0.0], [0.0, 0.0], [0.0, 0.0]])

@@ -14,6 +14,7 @@ from graphrole_b200.graph.generators import barabasi_albert_csr, erdos_renyi_csr
 from graphrole_b200.shard import (column_groups, cost_balanced_ranges, default_column_groups,
                                   exchange_rows, nnz_balanced_ranges, time_balanced_ranges)
 from oracle import refex_oracle as oracle
+from oracle import nmf_oracle
 
 
 def test_ranges_cover_all_rows_and_balance_arcs():
@@ -221,3 +222,80 @@ def test_column_groups_times_node_ranges_on_four_ranks():
     for rank in range(world):
         c0, c1, got = ret[rank]
         np.testing.assert_allclose(got, cur[:, c0:c1], rtol=1e-13, atol=0)
+
+
+# ---- path B: row-sharded NMF loop (roles/sharded.py) ------------------------------------------
+class _OracleNmfBackend:
+    """The three compute steps of RowShardedNmf done by the float64 oracle (CPU tensors)."""
+
+    def local_iteration(self, X, W, H, use_tf32=True):
+        Xn, Hn = X.numpy(), H.numpy()
+        Wn = nmf_oracle.update_w(Xn, W.numpy(), Hn)
+        W.copy_(torch.from_numpy(Wn))
+        return torch.from_numpy(np.concatenate([(Wn.T @ Xn).ravel(), (Wn.T @ Wn).ravel()]))
+
+    def update_h(self, sums, H):
+        r, f = H.shape
+        numer = sums[:r * f].numpy().reshape(r, f)
+        denom = sums[r * f:].numpy().reshape(r, r) @ H.numpy()
+        denom[denom == 0] = nmf_oracle.EPSILON
+        H.copy_(torch.from_numpy(H.numpy() * (numer / denom)))
+
+    def error_sq(self, X, W, H, use_tf32=True):
+        return nmf_oracle.frobenius_error(X.numpy(), W.numpy(), H.numpy()) ** 2
+
+
+def _nmf_problem():
+    rng = np.random.RandomState(4)
+    X = (rng.rand(700, 5) ** 2) @ rng.rand(5, 24) + 0.05 * rng.rand(700, 24)
+    return X, rng.rand(700, 4) + 0.1, rng.rand(4, 24) + 0.1
+
+
+def _nmf_worker(rank, world, port, ret):
+    from graphrole_b200.roles.sharded import RowShardedNmf, row_shard
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        X, W0, H0 = _nmf_problem()
+        lo, hi = row_shard(X.shape[0], world, rank, align=64)
+        Xl, Wl = torch.from_numpy(X[lo:hi].copy()), torch.from_numpy(W0[lo:hi].copy())
+        H = torch.from_numpy(H0.copy())
+        solver = RowShardedNmf(hi - lo, X.shape[1], 4, backend=_OracleNmfBackend())
+        n_iter, err = solver.fit(Xl, Wl, H, tol=2e-3)
+        ret[rank] = (lo, hi, Wl.numpy(), H.numpy(), n_iter, err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_row_sharded_nmf_loop_equals_single_process(world):
+    """RowShardedNmf.fit on gloo ranks (oracle compute): same factors, same stopping iteration
+    and same error as the single-process float64 loop -- the all-reduce of [W^T X | W^T W] and
+    of the squared residual is all that crosses the ranks; every rank ends with the same H."""
+    from graphrole_b200.roles.sharded import row_shard
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_nmf_worker, args=(world, port, ret), nprocs=world, join=True)
+    X, W0, H0 = _nmf_problem()
+    W, H, n_iter = nmf_oracle.fit_multiplicative_update(X, W0, H0, tol=2e-3)
+    err = nmf_oracle.frobenius_error(X, W, H)
+    covered = 0
+    for rank in range(world):
+        lo, hi, Wl, Hl, it, e = ret[rank]
+        assert (lo, hi) == row_shard(X.shape[0], world, rank, align=64)
+        covered += hi - lo
+        assert it == n_iter and it % 10 == 0 and it < 200
+        np.testing.assert_allclose(Wl, W[lo:hi], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Hl, H, rtol=1e-9, atol=1e-12)
+        np.testing.assert_array_equal(Hl, ret[0][3])
+        assert e == pytest.approx(err, rel=1e-10)
+    assert covered == X.shape[0]
+
+
+def test_row_shard_covers_all_rows_in_whole_blocks():
+    from graphrole_b200.roles.sharded import row_shard
+    for n, world in [(10_000_000, 8), (1000, 3), (129, 2), (5, 4)]:
+        spans = [row_shard(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % 128 == 0 for lo, _ in spans if lo < n)

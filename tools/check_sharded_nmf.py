@@ -1,0 +1,109 @@
+"""Row-sharded NMF (roles/sharded.py) under torchrun, one rank per GPU, NCCL: parity against the
+single-GPU library loop on the same matrix and -- with --bench -- ms per iteration of a C5-sized
+problem split by rows (strong scaling of hot path B).
+
+    torchrun --nproc-per-node N tools/check_sharded_nmf.py [--n ROWS] [--bench]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from graphrole_b200.roles import factor
+from graphrole_b200.roles.sharded import RowShardedNmf, nmf_mu_row_sharded, row_shard
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=300_000)
+    ap.add_argument('--f', type=int, default=512)
+    ap.add_argument('--bench', action='store_true')
+    ap.add_argument('--bench-n', type=int, default=10_000_000)
+    ap.add_argument('--ranks', default='8,32')
+    args = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ok = True
+    # ---- parity: the same matrix on every rank (same seed), rank r works on its rows
+    for r, use_tf32 in [(8, True), (5, True), (32, True), (6, False)]:
+        gen = torch.Generator(device=dev).manual_seed(7)
+        n, f = args.n, args.f
+        X = torch.rand(n, 6, device=dev, generator=gen).square_() @ torch.rand(6, f, device=dev, generator=gen)
+        X += 0.05 * torch.rand(n, f, device=dev, generator=gen)
+        W0 = torch.rand(n, r, device=dev, generator=gen) + 0.1
+        H0 = torch.rand(r, f, device=dev, generator=gen) + 0.1
+        lo, hi = row_shard(n, world, rank)
+        Wl, H, it_s, err_s = nmf_mu_row_sharded(X[lo:hi], W0[lo:hi].contiguous(), H0, max_iter=40,
+                                                 use_tf32=use_tf32)
+        Wu, Hu, it_u, err_u = factor.nmf_mu(X, W0, H0, max_iter=40, use_tf32=use_tf32)
+        dw = float((Wl - Wu[lo:hi]).abs().max() / Wu.abs().max())
+        dh = float((H - Hu).abs().max() / Hu.abs().max())
+        same_h = True
+        if world > 1:
+            Hs = [torch.empty_like(H) for _ in range(world)]
+            dist.all_gather(Hs, H)
+            same_h = all(torch.equal(h, Hs[0]) for h in Hs)
+        # tcgen05 path: W is held at TF32 precision, a last-bit difference in H (order of the
+        # partial sums across ranks) can flip the rounding of an entry of W by 2^-11 of its value
+        tol_w, tol_h = (4e-3, 5e-4) if use_tf32 else (2e-4, 2e-4)
+        good = it_s == it_u and dw < tol_w and dh < tol_h and abs(err_s - err_u) <= 1e-5 * err_u and same_h
+        ok &= good
+        if rank == 0:
+            print(json.dumps({'r': r, 'use_tf32': use_tf32, 'world': world, 'rows': [lo, hi],
+                              'n_iter': [it_s, it_u], 'rel_dW': dw, 'rel_dH': dh,
+                              'err': [err_s, err_u], 'H_identical_on_all_ranks': same_h,
+                              'ok': good}), flush=True)
+        del X, W0, H0, Wl, H, Wu, Hu
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print('SHARDED NMF CHECK OK' if int(flag) else 'SHARDED NMF CHECK FAILED', flush=True)
+    # ---- strong scaling of C5: n rows split over the ranks
+    if args.bench:
+        n, f = args.bench_n, args.f
+        lo, hi = row_shard(n, world, rank)
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        X = torch.rand(hi - lo, f, device=dev, generator=gen)
+        for r in [int(v) for v in args.ranks.split(',')]:
+            W = torch.rand(hi - lo, r, device=dev, generator=gen) + 0.1
+            H = torch.rand(r, f, device=dev, generator=torch.Generator(device=dev).manual_seed(99)) + 0.1
+            solver = RowShardedNmf(hi - lo, f, r, dev)
+            solver.fit(X, W, H, max_iter=3, tol=0)
+            out = {}
+            for label, kw, iters in (('ms_per_iter', dict(tol=0), 20),
+                                     ('ms_per_iter_with_checks', dict(tol=1e-30, check_every=10), 20)):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                n_it, _ = solver.fit(X, W, H, max_iter=iters, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / max(n_it, 1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out[label] = round(float(t), 4)
+            if rank == 0:
+                print(json.dumps({'bench': 'C5 rows split over the ranks', 'n': n, 'f': f, 'r': r,
+                                  'world': world, 'rows_per_rank': hi - lo, **out,
+                                  'allreduce_bytes_per_iteration': solver.allreduce_bytes_per_iteration,
+                                  'path': solver.backend.last_path}), flush=True)
+            solver.close()
+            del W, H
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == '__main__':
+    main()
