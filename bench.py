@@ -506,6 +506,11 @@ def run_gpu_arm(args):
         except Exception as exc:      # never lose the headline line to the secondary section
             line['nmf'] = {'error': repr(exc)}
 
+    # ---- hot path B row-sharded over the ranks (N > 1) -------------------
+    if world > 1 and not args.no_nmf:
+        torch.cuda.empty_cache()
+        line['nmf_row_sharded'] = nmf_row_sharded_section(device, dist, rank, world)
+
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -748,6 +753,61 @@ def nmf_section(device, n=10_000_000, f=512, ranks=(2, 4, 5, 8, 16, 32), iters=1
                                   'cores': os.cpu_count()}
     except Exception as exc:
         out['cpu_sklearn_f64'] = {'error': repr(exc)}
+    return out
+
+
+def nmf_row_sharded_section(device, dist, rank, world, n=10_000_000, f=512, ranks=(8, 32),
+                            iters=20):
+    """C5 with its rows split over the ranks (strong scaling of hot path B): H replicated, one
+    NCCL all-reduce of [W^T X | W^T W] per iteration (roles/sharded.py).  Every rank reaches the
+    collectives together or not at all: set-up is voted on first."""
+    from graphrole_b200.roles.sharded import RowShardedNmf, row_shard
+    lo, hi = row_shard(n, world, rank)
+    out = {'workload': f'X {n}x{f} fp32 U[0,1) split by rows over {world} ranks, H replicated',
+           'rows_per_rank': hi - lo, 'per_rank': []}
+    X = solver = None
+    ok = torch.ones(1, device=device)
+    try:
+        gen = torch.Generator(device=device).manual_seed(100 + rank)
+        X = torch.rand(hi - lo, f, device=device, generator=gen)
+    except Exception as exc:
+        out['error'] = repr(exc)
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not bool(ok.item()):
+        out.setdefault('error', 'set-up failed on another rank')
+        return out
+    for r in ranks:
+        ok.fill_(1)
+        try:
+            W = torch.rand(hi - lo, r, device=device, generator=gen) + 0.1
+            H = torch.rand(r, f, device=device,
+                           generator=torch.Generator(device=device).manual_seed(99)) + 0.1
+            solver = RowShardedNmf(hi - lo, f, r, device)
+        except Exception as exc:
+            out['error'] = repr(exc)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            break
+        solver.fit(X, W, H, max_iter=3, tol=0)
+        row = {'r': r, 'path': solver.backend.last_path,
+               'allreduce_bytes_per_iteration': solver.allreduce_bytes_per_iteration}
+        for key, kw in (('ms_per_iter', dict(tol=0)),
+                        ('ms_per_iter_with_convergence_checks', dict(tol=1e-30, check_every=10))):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n_it, _ = solver.fit(X, W, H, max_iter=iters, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / max(n_it, 1)], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            row[key] = float(t.item())
+        out['per_rank'].append(row)
+        solver.close()
+        del W, H
     return out
 
 
