@@ -14,6 +14,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <vector>
 
 #define CU(x)                                                                         \
@@ -177,6 +178,47 @@ int main(int argc, char** argv) {
     }
     printf("peer stores  : %zu MiB to %d replicas in %.3f ms = %.1f GB/s of payload (%.1f GB/s on the wire)\n",
            size >> 20, n_dev, ms, (double)size / ms / 1e6, (double)size * (n_dev - 1) / ms / 1e6);
+
+    // ---- the exchange itself: EVERY device multicasts its own 1/n slice at the same time (an
+    // all-gather by multicast); what bounds it is each device's ingress of (n-1)/n of the object
+    {
+        const size_t slice_vec = n_vec / n_dev;
+        std::vector<cudaStream_t> st(n_dev);
+        for (int d = 0; d < n_dev; ++d) { RT(cudaSetDevice(d)); RT(cudaStreamCreate(&st[d])); }
+        double best_mc = 1e30, best_uc = 1e30;
+        for (int rep = 0; rep < 3; ++rep) {
+            for (int mode = 0; mode < 2; ++mode) {
+                for (int d = 0; d < n_dev; ++d) { RT(cudaSetDevice(d)); RT(cudaDeviceSynchronize()); }
+                timespec t0, t1;
+                clock_gettime(CLOCK_MONOTONIC, &t0);
+                for (int d = 0; d < n_dev; ++d) {
+                    RT(cudaSetDevice(d));
+                    if (mode == 0) {
+                        mc_store_kernel<<<148 * 8, 256, 0, st[d]>>>(
+                            (float4*)mcva[d] + (size_t)d * slice_vec, slice_vec, 6.0f);
+                    } else {
+                        Ptrs pp;
+                        pp.n = n_dev;
+                        for (int q = 0; q < n_dev; ++q) pp.p[q] = (float4*)uc[q] + (size_t)d * slice_vec;
+                        uc_store_kernel<<<148 * 8, 256, 0, st[d]>>>(pp, slice_vec, 7.0f);
+                    }
+                }
+                for (int d = 0; d < n_dev; ++d) { RT(cudaSetDevice(d)); RT(cudaStreamSynchronize(st[d])); }
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                const double dt = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6;
+                if (mode == 0) best_mc = dt < best_mc ? dt : best_mc;
+                else best_uc = dt < best_uc ? dt : best_uc;
+            }
+        }
+        const double slice_bytes = (double)slice_vec * sizeof(float4);
+        const double ingress = slice_bytes * (n_dev - 1);
+        printf("all devices at once, %d slices of %.1f MiB (host-timed, best of 3):\n", n_dev,
+               slice_bytes / 1048576.0);
+        printf("  multimem.st : %.3f ms = %.1f GB/s ingress per device, %.1f GB/s egress per device\n",
+               best_mc, ingress / best_mc / 1e6, slice_bytes / best_mc / 1e6);
+        printf("  peer stores : %.3f ms = %.1f GB/s ingress per device, %.1f GB/s egress per device\n",
+               best_uc, ingress / best_uc / 1e6, ingress / best_uc / 1e6);
+    }
     printf("RESULT: done\n");
     return 0;
 }
