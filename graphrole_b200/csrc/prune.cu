@@ -6,11 +6,15 @@
 // prune.py:104-108).  Both steps are O(n) per column / column pair and run between every pair of
 // recursion levels (extract.py:135-137).  Here:
 //
-//   binning   per column: cub radix sort of (value, row) pairs; one warp walks the bin boundaries
+//   binning   per column: cub radix sort of the VALUES alone; one warp walks the bin boundaries
 //             (each boundary = end of the run of equal values that contains sorted position
 //             want-1, found by a 32-ary search) -- the same integers the reference gets from
-//             searchsorted(cumsum(counts), binned_len + bin_size); every sorted position then
-//             looks its bin up among the boundaries and scatters it to the row it came from.
+//             searchsorted(cumsum(counts), binned_len + bin_size) -- and records every bin's
+//             largest value.  Bins end on run ends, so a value's bin is the number of bins whose
+//             largest value lies below it: every row looks its own value up among those (<= a
+//             few dozen) thresholds, reading and writing in row order.  (Round 1 sorted
+//             (value, row) pairs and scattered the bin of every sorted position back to its
+//             row: twice the sort traffic plus n random 4-byte stores per column.)
 //             Columns are pulled out of the row-major feature matrix 32 (fp32) / 16 (fp64) at a
 //             time through a shared-memory transpose, so the matrix is read once, coalesced.
 //   distance  persistent CTAs stream row chunks of ALL binned columns through shared memory and
@@ -18,7 +22,7 @@
 //             registers (bins are small integers, exact in fp32: |a - b| folds into FADD's
 //             operand modifiers + FMNMX); one atomicMax per pair per CTA at the end.
 //
-// Bound: binning is sort-bound (cub, ~16 bytes moved per key per pass); the distance kernel is
+// Bound: binning is sort-bound (cub, ~8 bytes moved per key per pass); the distance kernel is
 // ALU-bound at 2 instructions per (pair, row) -- F^2/2 * n * 2 lane-ops, e.g. F = 128, n = 10 M:
 // 1.6e11 lane-ops ~ 5 ms on 148 SMs -- while reading the binned matrix (F * n * 4 bytes) once per
 // batch of 256 pair tiles.
@@ -39,8 +43,7 @@ struct gr_pruner {
     int max_smem = 0;
     void* colbuf = nullptr;      // [32][n] fp32 or [16][n] fp64: the column group being binned
     void* keys_sorted = nullptr; // [n] of the key type (8 bytes per entry reserved)
-    int32_t* iota = nullptr;     // [n] 0..n-1
-    int32_t* rows_sorted = nullptr;  // [n]
+    void* tops = nullptr;        // [n + 1] of the key type: largest value of every bin
     int32_t* bounds = nullptr;   // [n + 1] bin boundaries (exclusive end positions), ascending
     int32_t* n_bounds = nullptr; // [1]
     void* cub_temp = nullptr;
@@ -75,17 +78,13 @@ __global__ void extract_columns_kernel(const T* __restrict__ X, int64_t ldx, int
     }
 }
 
-__global__ void iota_kernel(int32_t* p, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (int32_t)i;
-}
-
 // ---- bin boundaries: one warp, 32-ary upper-bound searches ----------------------------------------
 // Follows prune.py:36-54: bin_size = max(int(frac * unbinned), 1); the bin ends with the run of
 // equal values containing sorted position binned + bin_size - 1.
 template <typename T>
 __global__ void bin_bounds_kernel(const T* __restrict__ keys, int64_t n, double frac,
-                                  int32_t* __restrict__ bounds, int32_t* __restrict__ n_bounds) {
+                                  int32_t* __restrict__ bounds, T* __restrict__ tops,
+                                  int32_t* __restrict__ n_bounds) {
     const int lane = threadIdx.x;
     int64_t done = 0;
     int nb = 0;
@@ -95,6 +94,19 @@ __global__ void bin_bounds_kernel(const T* __restrict__ keys, int64_t n, double 
         const T v = keys[want - 1];
         // first position p in [want, n] with p == n or keys[p] > v (keys ascending; -0.0 == 0.0)
         int64_t lo = want, hi = n;                        // answer in [lo, hi]
+        {
+            // galloping first round: probes at want + 2^lane - 1.  A column of distinct values
+            // ends the search here (lane 0 already sees a larger key) -- one dependent load per
+            // bin instead of log32(n) rounds; a tie of length t leaves a range of <= t to search.
+            const int64_t off = lane < 31 ? (((int64_t)1 << lane) - 1) : (int64_t)1 << 40;
+            const int64_t p = want + off;
+            const bool greater = p < n ? (keys[p] > v) : true;
+            const unsigned m = __ballot_sync(0xffffffffu, greater);     // lane 31 always votes
+            const int first = __ffs(m) - 1;
+            const int64_t pf = want + (first < 31 ? (((int64_t)1 << first) - 1) : (int64_t)1 << 40);
+            if (first > 0) lo = want + (((int64_t)1 << (first - 1)) - 1) + 1;
+            hi = pf < n ? pf : n;
+        }
         while (lo < hi) {
             const int64_t span = hi - lo;
             const int64_t step = (span + 31) / 32;        // 32 ascending probes cover [lo, hi)
@@ -111,32 +123,35 @@ __global__ void bin_bounds_kernel(const T* __restrict__ keys, int64_t n, double 
             hi = pf < hi ? pf : hi;
         }
         done = lo;
-        if (lane == 0) bounds[nb] = (int32_t)done;
+        if (lane == 0) {
+            bounds[nb] = (int32_t)done;
+            tops[nb] = v;          // the bin holds exactly the values in (tops[nb - 1], v]
+        }
         ++nb;
     }
     if (lane == 0) *n_bounds = nb;
 }
 
-// ---- bin of every sorted position, scattered back to its row ---------------------------------------
-__global__ void assign_bins_kernel(const int32_t* __restrict__ rows_sorted,
-                                   const int32_t* __restrict__ bounds,
+// ---- bin of every row: number of bins whose largest value is below the row's value --------------
+template <typename T>
+__global__ void assign_bins_kernel(const T* __restrict__ values, const T* __restrict__ tops,
                                    const int32_t* __restrict__ n_bounds, int64_t n,
                                    int32_t* __restrict__ bins_col) {
-    __shared__ int32_t sb[1024];
+    __shared__ T st[512];
     const int nb = *n_bounds;
-    const int cached = min(nb, 1024);
-    for (int i = threadIdx.x; i < cached; i += blockDim.x) sb[i] = bounds[i];
+    const int cached = min(nb, 512);
+    for (int i = threadIdx.x; i < cached; i += blockDim.x) st[i] = tops[i];
     __syncthreads();
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    // bin = number of boundaries <= p  (boundaries are exclusive end positions)
-    int lo = 0, hi = nb;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const T x = values[r];
+    int lo = 0, hi = nb;           // first bin whose largest value is >= x (== compares -0.0, 0.0)
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int32_t b = mid < cached ? sb[mid] : bounds[mid];
-        if ((int64_t)b <= p) lo = mid + 1; else hi = mid;
+        const T t = mid < cached ? st[mid] : tops[mid];
+        if (t < x) lo = mid + 1; else hi = mid;
     }
-    bins_col[rows_sorted[p]] = lo;
+    bins_col[r] = lo;
 }
 
 // ---- pairwise Chebyshev distance of binned columns --------------------------------------------------
@@ -228,6 +243,7 @@ int bin_columns(gr_pruner* h, const T* X, int64_t ldx, int32_t d, double frac, i
     const int64_t n = h->n;
     T* colbuf = static_cast<T*>(h->colbuf);
     T* keys_sorted = static_cast<T*>(h->keys_sorted);
+    T* tops = static_cast<T*>(h->tops);
     const unsigned blocks_n = (unsigned)ceil_div<int64_t>(n, 256);
     for (int c0 = 0; c0 < d; c0 += G) {
         const int cols = std::min(G, d - c0);
@@ -236,12 +252,14 @@ int bin_columns(gr_pruner* h, const T* X, int64_t ldx, int32_t d, double frac, i
         count_launch();
         for (int c = 0; c < cols; ++c) {
             size_t temp = h->cub_temp_bytes;
-            GR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->cub_temp, temp, colbuf + (int64_t)c * n,
-                                                        keys_sorted, h->iota, h->rows_sorted,
-                                                        (int)n, 0, (int)sizeof(T) * 8, st));
-            bin_bounds_kernel<T><<<1, 32, 0, st>>>(keys_sorted, n, frac, h->bounds, h->n_bounds);
-            assign_bins_kernel<<<blocks_n, 256, 0, st>>>(h->rows_sorted, h->bounds, h->n_bounds, n,
-                                                         bins + (int64_t)(c0 + c) * ldb);
+            GR_CUDA_TRY(cub::DeviceRadixSort::SortKeys(h->cub_temp, temp, colbuf + (int64_t)c * n,
+                                                       keys_sorted, (int)n, 0, (int)sizeof(T) * 8,
+                                                       st));
+            bin_bounds_kernel<T><<<1, 32, 0, st>>>(keys_sorted, n, frac, h->bounds, tops,
+                                                   h->n_bounds);
+            assign_bins_kernel<T><<<blocks_n, 256, 0, st>>>(colbuf + (int64_t)c * n, tops,
+                                                            h->n_bounds, n,
+                                                            bins + (int64_t)(c0 + c) * ldb);
             count_launch(2);
         }
     }
@@ -268,10 +286,10 @@ extern "C" int gr_pruner_create(gr_pruner_t** out, int64_t n_rows, int device) {
     cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     size_t t32 = 0, t64 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t32, (const float*)nullptr, (float*)nullptr,
-                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows);
-    cub::DeviceRadixSort::SortPairs(nullptr, t64, (const double*)nullptr, (double*)nullptr,
-                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows);
+    cub::DeviceRadixSort::SortKeys(nullptr, t32, (const float*)nullptr, (float*)nullptr,
+                                   (int)n_rows);
+    cub::DeviceRadixSort::SortKeys(nullptr, t64, (const double*)nullptr, (double*)nullptr,
+                                   (int)n_rows);
     h->cub_temp_bytes = std::max(t32, t64);
     const size_t n = (size_t)n_rows;
     cudaError_t e = cudaSuccess;
@@ -280,8 +298,7 @@ extern "C" int gr_pruner_create(gr_pruner_t** out, int64_t n_rows, int device) {
     };
     alloc(&h->colbuf, n * kGroupBytes);
     alloc(&h->keys_sorted, n * 8);
-    alloc((void**)&h->iota, n * 4);
-    alloc((void**)&h->rows_sorted, n * 4);
+    alloc(&h->tops, (n + 1) * 8);
     alloc((void**)&h->bounds, (n + 1) * 4);
     alloc((void**)&h->n_bounds, 4);
     alloc(&h->cub_temp, std::max<size_t>(h->cub_temp_bytes, 16));
@@ -291,8 +308,6 @@ extern "C" int gr_pruner_create(gr_pruner_t** out, int64_t n_rows, int device) {
         return fail(e == cudaErrorMemoryAllocation ? GR_ERR_OUT_OF_MEMORY : GR_ERR_CUDA,
                     "gr_pruner_create: workspace allocation failed: %s", cudaGetErrorString(e));
     }
-    iota_kernel<<<(unsigned)ceil_div<int64_t>(n_rows, 256), 256>>>(h->iota, n_rows);
-    count_launch();
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         gr_pruner_destroy(h);
@@ -307,8 +322,7 @@ extern "C" int gr_pruner_destroy(gr_pruner_t* h) {
     DeviceGuard guard(h->device);
     cudaFree(h->colbuf);
     cudaFree(h->keys_sorted);
-    cudaFree(h->iota);
-    cudaFree(h->rows_sorted);
+    cudaFree(h->tops);
     cudaFree(h->bounds);
     cudaFree(h->n_bounds);
     cudaFree(h->cub_temp);
