@@ -746,11 +746,28 @@ def nmf_section(device, n=10_000_000, f=512, ranks=(2, 4, 5, 8, 16, 32), iters=1
         rng = np.random.RandomState(0)
         W0, H0 = rng.rand(m, 32) + 0.1, rng.rand(32, f) + 0.1
         t0 = time.perf_counter()
-        sk._fit_multiplicative_update(Xc, W0, H0, 'frobenius', max_iter=2, tol=0)
+        W_sk, H_sk, _ = sk._fit_multiplicative_update(Xc, W0.copy(), H0.copy(), 'frobenius',
+                                                      max_iter=2, tol=0)
         dt = (time.perf_counter() - t0) / 2
         out['cpu_sklearn_f64'] = {'r': 32, 'rows': m, 's_per_iter_sample': dt,
                                   's_per_iter_scaled_to_n': dt * n / m,
                                   'cores': os.cpu_count()}
+        # parity of what was timed: the same rows, the same start, the same two iterations through
+        # the tcgen05 kernels against scikit-learn's own loop (TF32 tolerance of the tests: 1e-2
+        # of the factor's largest entry; error 1e-3)
+        Wg, Hg, _, err_g = factor.nmf_mu(
+            X[:m], torch.as_tensor(W0, dtype=torch.float32, device=device),
+            torch.as_tensor(H0, dtype=torch.float32, device=device), max_iter=2, tol=0)
+        dw = float(np.abs(Wg.double().cpu().numpy() - W_sk).max() / np.abs(W_sk).max())
+        dh = float(np.abs(Hg.double().cpu().numpy() - H_sk).max() / np.abs(H_sk).max())
+        err_sk = float(np.linalg.norm(Xc - W_sk @ H_sk))
+        out['parity'] = {'against': 'sklearn _fit_multiplicative_update (float64), same rows / '
+                                    'start / iterations', 'rows': m, 'r': 32, 'iterations': 2,
+                         'path': factor.last_path, 'rel_dW': dw, 'rel_dH': dh,
+                         'error': err_g, 'error_sklearn': err_sk, 'tolerance': 1e-2,
+                         'ok': bool(dw < 1e-2 and dh < 1e-2 and
+                                    abs(err_g - err_sk) <= 1e-3 * err_sk and
+                                    factor.last_path == 'tcgen05')}
     except Exception as exc:
         out['cpu_sklearn_f64'] = {'error': repr(exc)}
     return out
@@ -805,6 +822,11 @@ def nmf_row_sharded_section(device, dist, rank, world, n=10_000_000, f=512, rank
             t = torch.tensor([e0.elapsed_time(e1) / max(n_it, 1)], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             row[key] = float(t.item())
+        # parity of what was timed: H is replicated, so every rank must hold the same bits
+        Hs = [torch.empty_like(H) for _ in range(world)]
+        dist.all_gather(Hs, H)
+        row['H_identical_on_all_ranks'] = all(torch.equal(h, Hs[0]) for h in Hs)
+        row['H_finite_nonnegative'] = bool(torch.isfinite(H).all() and (H >= 0).all())
         out['per_rank'].append(row)
         solver.close()
         del W, H
