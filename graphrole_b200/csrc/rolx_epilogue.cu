@@ -13,9 +13,17 @@
 // the sorted values) and k prefix-sum differences -- microseconds, independent of n -- so the whole
 // Lloyd loop, its convergence tests and the empty-cluster relocation run inside a single one-CTA
 // kernel launch, and the sort is shared by all the n_bins values the grid tries on one factor.
-// What stays O(n) per centre is sklearn's k-means++ seeding, which samples positions of the
-// ORIGINAL order proportionally to the squared distance to the nearest chosen centre: one scan,
-// one fused candidate evaluation and one update pass per centre, all HBM streaming kernels.
+// sklearn's k-means++ seeding samples positions of the ORIGINAL order proportionally to the
+// squared distance to the nearest chosen centre, which needs sums over that order: one streaming
+// pass (8 bytes per entry) per centre for block sums of those distances.  Everything else about a
+// new centre is local in the SORTED order: a candidate c between the existing centres c_L < c <
+// c_R can only win points with c_L < x < c_R (for x <= c_L sklearn's rounded squared distance to
+// c exceeds the one to c_L as soon as (c - c_L)^2 is above the rounding noise of the expansion
+// x^2 - 2xc + c^2; closer candidates fall back to the whole range), so candidate potentials and
+// the distance update touch only that range of the sorted values (through the sort
+// permutation) -- about 2n/k entries per centre instead of n per candidate.  At 256 bins this
+// is 40 x less traffic than round 2's first form (one scan, one fused candidate evaluation and
+// one update pass over all entries per centre).
 // The random stream is NumPy's RandomState(seed) (mt19937.h), so labels equal scikit-learn's
 // whenever the data hold at least n_bins distinct values (otherwise scikit-learn's own result
 // depends on np.argpartition's order of equal keys; here every distinct value becomes a level).
@@ -39,6 +47,9 @@ constexpr int kMaxBins = 1024;
 constexpr int kMaxTrials = 8;          // 2 + int(ln(1024))
 constexpr int kRedBlocks = 148 * 4;    // fixed grid of the deterministic two-stage reductions
 constexpr int kRedThreads = 256;
+constexpr int kPpBlock = 4096;         // k-means++: entries per block sum (original order)
+constexpr int kPpStreamRounds = 20;    // centres 1 .. 19 are evaluated by streaming passes (measured: a range gather of
+                                       // 4 - 7 candidates costs more than the stream while ranges hold > ~N/12 entries)
 
 }  // namespace
 
@@ -55,7 +66,9 @@ struct gr_quantizer {
     double* xs = nullptr;       // the same values sorted ascending
     double* P = nullptr;        // [N + 1] exclusive prefix sums of xs
     double* closest = nullptr;  // k-means++: squared distance to the nearest chosen centre
-    double* cum = nullptr;      // k-means++: inclusive scan of `closest`
+    int64_t* perm = nullptr;    // sorted position -> original position
+    double* bsum = nullptr;     // k-means++: (cumulative) sums of `closest` per kPpBlock entries
+    double* centres_sorted = nullptr;  // [kMaxBins] chosen centres, ascending
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
     double* partial = nullptr;  // [kRedBlocks * kMaxTrials]
@@ -153,28 +166,188 @@ pp_init_kernel(const double* __restrict__ x, int64_t N, double c, double* __rest
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// candidate_ids = clip(searchsorted(cumsum(closest), rand_vals), n - 1)  (_kmeans.py:250-254)
-__global__ void pp_search_kernel(const double* __restrict__ cum, const double* __restrict__ x,
-                                 int64_t N, const double* __restrict__ rand_vals, int trials,
-                                 int64_t* __restrict__ cand_idx, double* __restrict__ cand_x) {
-    const int t = threadIdx.x;
-    if (t >= trials) return;
-    const double v = rand_vals[t];
-    int64_t lo = 0, hi = N;                 // first index with cum[idx] >= v
-    while (lo < hi) {
-        const int64_t mid = lo + (hi - lo) / 2;
-        if (cum[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    lo = min(lo, N - 1);
-    cand_idx[t] = lo;
-    cand_x[t] = x[lo];
+__global__ void iota64_kernel(int64_t* p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
-// candidates_pot[t] = sum_i min(closest[i], dist(x[cand_t], x[i]))  (_kmeans.py:257-263)
+// sums of `closest` over blocks of kPpBlock entries of the original order, fixed order
+__global__ void __launch_bounds__(kRedThreads)
+pp_block_sums_kernel(const double* __restrict__ closest, int64_t N, double* __restrict__ bsum) {
+    const int64_t base = (int64_t)blockIdx.x * kPpBlock;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < kPpBlock; j += kRedThreads) {
+        const int64_t i = base + j;
+        if (i < N) acc += closest[i];
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = t;
+}
+
+// One CTA.  (1) bsum -> its inclusive cumulative sums, pot = their total (current_pot,
+// _kmeans.py:246); (2) candidate_ids = clip(searchsorted(cumsum(closest), rand * pot), n - 1)
+// (_kmeans.py:250-254): the block by binary search, the entry by a sequential sum inside the
+// block; (3) per candidate the range [lo, hi) of SORTED positions its centre could win: the
+// values strictly between the neighbouring chosen centres -- empty when the value is a centre
+// already, everything when a neighbour is within rounding noise of it.
+__global__ void __launch_bounds__(1024)
+pp_scan_search_kernel(double* __restrict__ bsum, int nblk, const double* __restrict__ closest,
+                      const double* __restrict__ x, const double* __restrict__ xs, int64_t N,
+                      const double* __restrict__ u, int trials,
+                      const double* __restrict__ centres_sorted, int n_centres,
+                      int64_t* __restrict__ cand_idx, double* __restrict__ cand_x,
+                      int64_t* __restrict__ cand_lo, int64_t* __restrict__ cand_hi,
+                      double* __restrict__ pot_out) {
+    __shared__ double slice_tot[1024];
+    __shared__ double pot_s;
+    int t = threadIdx.x;
+    const int per = (nblk + 1023) / 1024;
+    const int b0 = min(nblk, t * per), b1 = min(nblk, b0 + per);
+    double run = 0.0;
+    for (int b = b0; b < b1; ++b) { run += bsum[b]; bsum[b] = run; }
+    slice_tot[t] = run;
+    __syncthreads();
+    if (t == 0) {
+        double off = 0.0;
+        for (int q = 0; q < 1024; ++q) { const double v = slice_tot[q]; slice_tot[q] = off; off += v; }
+        pot_s = off;
+        *pot_out = off;
+    }
+    __syncthreads();
+    const double off = slice_tot[t];
+    if (off != 0.0)
+        for (int b = b0; b < b1; ++b) bsum[b] += off;
+    __syncthreads();
+    // one warp per candidate from here on
+    const int w = t >> 5, lane = t & 31;
+    if (w >= trials) return;
+    const double pot = pot_s;
+    const double v = __dmul_rn(u[w], pot);
+    int lo_b = 0, hi_b = nblk;               // first block whose cumulative sum reaches v
+    while (lo_b < hi_b) {
+        const int mid = (lo_b + hi_b) >> 1;
+        if (bsum[mid] < v) lo_b = mid + 1; else hi_b = mid;
+    }
+    int64_t idx = N - 1;
+    if (lo_b < nblk) {
+        // The entry inside the block, three levels of 32 so that no thread walks memory
+        // serially (a single thread summing 4096 entries with an early exit cost ~1 ms per
+        // centre): 32 segments of 128, the crossing segment as 32 groups of 4, then 4 entries.
+        const double base = lo_b > 0 ? bsum[lo_b - 1] : 0.0;
+        const int64_t i0 = (int64_t)lo_b * kPpBlock, i1 = min(N, i0 + kPpBlock);
+        auto warp_prefix = [&](double s, double& excl) {       // fixed order, lane by lane
+            double incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0.0;
+            return incl;
+        };
+        double s1 = 0.0;
+        for (int j = 0; j < kPpBlock / 32; ++j) {
+            const int64_t i = i0 + (int64_t)lane * (kPpBlock / 32) + j;
+            if (i < i1) s1 += closest[i];
+        }
+        double excl1;
+        const double incl1 = warp_prefix(s1, excl1);
+        const unsigned m1 = __ballot_sync(0xffffffffu, base + incl1 >= v);
+        idx = i1 - 1;
+        if (m1 != 0) {
+            const int l1 = __ffs(m1) - 1;
+            const double acc1 = base + __shfl_sync(0xffffffffu, excl1, l1);
+            const int64_t seg0 = i0 + (int64_t)l1 * (kPpBlock / 32);
+            double e[4], s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t i = seg0 + lane * 4 + j;
+                e[j] = i < i1 ? closest[i] : 0.0;
+                s2 += e[j];
+            }
+            double excl2;
+            const double incl2 = warp_prefix(s2, excl2);
+            const unsigned m2 = __ballot_sync(0xffffffffu, acc1 + incl2 >= v);
+            idx = min(seg0 + kPpBlock / 32 - 1, i1 - 1);
+            if (m2 != 0) {
+                const int l2 = __ffs(m2) - 1;
+                double acc2 = acc1 + __shfl_sync(0xffffffffu, excl2, l2);
+                idx = min(seg0 + l2 * 4 + 3, i1 - 1);
+                bool found = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc2 += __shfl_sync(0xffffffffu, e[j], l2);
+                    if (!found && acc2 >= v) { idx = min(seg0 + l2 * 4 + j, i1 - 1); found = true; }
+                }
+            }
+        }
+    }
+    if (lane != 0) return;
+    t = w;
+    const double c = x[idx];
+    cand_idx[t] = idx;
+    cand_x[t] = c;
+    int pos = 0, hi_c = n_centres;           // first chosen centre >= c
+    while (pos < hi_c) {
+        const int mid = (pos + hi_c) >> 1;
+        if (centres_sorted[mid] < c) pos = mid + 1; else hi_c = mid;
+    }
+    int64_t lo = 0, hi = 0;
+    if (!(pos < n_centres && centres_sorted[pos] == c)) {
+        const double m2 = fmax(xs[0] * xs[0], xs[N - 1] * xs[N - 1]);
+        const double guard = 1e-14 * m2;
+        const bool has_l = pos > 0, has_r = pos < n_centres;
+        const double cl = has_l ? centres_sorted[pos - 1] : 0.0;
+        const double cr = has_r ? centres_sorted[pos] : 0.0;
+        const bool everything = (has_l && (c - cl) * (c - cl) <= guard) ||
+                                (has_r && (cr - c) * (cr - c) <= guard);
+        lo = 0;
+        hi = N;
+        if (!everything) {
+            if (has_l) {                     // first sorted value > cl
+                int64_t a = 0, b = N;
+                while (a < b) { const int64_t m = a + (b - a) / 2; if (xs[m] <= cl) a = m + 1; else b = m; }
+                lo = a;
+            }
+            if (has_r) {                     // first sorted value >= cr
+                int64_t a = 0, b = N;
+                while (a < b) { const int64_t m = a + (b - a) / 2; if (xs[m] < cr) a = m + 1; else b = m; }
+                hi = a;
+            }
+        }
+    }
+    cand_lo[t] = lo;
+    cand_hi[t] = hi;
+}
+
+// what candidate t would take off the potential: sum over its range of
+// closest - min(closest, dist(c_t, x))  (candidates_pot = pot - that, _kmeans.py:257-263)
+__global__ void __launch_bounds__(kRedThreads)
+pp_eval_range_kernel(const double* __restrict__ xs, const int64_t* __restrict__ perm,
+                     const double* __restrict__ closest, const double* __restrict__ cand_x,
+                     const int64_t* __restrict__ cand_lo, const int64_t* __restrict__ cand_hi,
+                     double* __restrict__ partial) {
+    const int t = blockIdx.y;
+    const double c = cand_x[t], cc = __dmul_rn(c, c);
+    const int64_t hi = cand_hi[t];
+    double acc = 0.0;
+    for (int64_t p = cand_lo[t] + (int64_t)blockIdx.x * kRedThreads + threadIdx.x; p < hi;
+         p += (int64_t)gridDim.x * kRedThreads) {
+        const double cl = closest[perm[p]];
+        acc += cl - fmin(cl, sk_sqdist(c, cc, xs[p]));
+    }
+    const double s = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x * kMaxTrials + t] = s;
+}
+
+// The same two steps as streaming passes over ALL entries in their original order: what the first
+// few centres use, whose ranges are most of the data (a gather through the permutation moves a
+// 32-byte sector per 8-byte value; a stream does not).
 template <int TRIALS>
 __global__ void __launch_bounds__(kRedThreads)
-pp_eval_kernel(const double* __restrict__ x, const double* __restrict__ closest, int64_t N,
-               const double* __restrict__ cand_x, double* __restrict__ partial) {
+pp_eval_all_kernel(const double* __restrict__ x, const double* __restrict__ closest, int64_t N,
+                   const double* __restrict__ cand_x, double* __restrict__ partial) {
     double c[TRIALS], cc[TRIALS], acc[TRIALS];
 #pragma unroll
     for (int t = 0; t < TRIALS; ++t) {
@@ -186,7 +359,7 @@ pp_eval_kernel(const double* __restrict__ x, const double* __restrict__ closest,
          i += (int64_t)gridDim.x * kRedThreads) {
         const double xi = x[i], cl = closest[i];
 #pragma unroll
-        for (int t = 0; t < TRIALS; ++t) acc[t] += fmin(cl, sk_sqdist(c[t], cc[t], xi));
+        for (int t = 0; t < TRIALS; ++t) acc[t] += cl - fmin(cl, sk_sqdist(c[t], cc[t], xi));
     }
 #pragma unroll
     for (int t = 0; t < TRIALS; ++t) {
@@ -196,11 +369,24 @@ pp_eval_kernel(const double* __restrict__ x, const double* __restrict__ closest,
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-pp_update_kernel(const double* __restrict__ x, int64_t N, double c, double* __restrict__ closest) {
+pp_update_all_kernel(const double* __restrict__ x, int64_t N, double c,
+                     double* __restrict__ closest) {
     const double cc = __dmul_rn(c, c);
     for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < N;
          i += (int64_t)gridDim.x * kRedThreads)
         closest[i] = fmin(closest[i], sk_sqdist(c, cc, x[i]));
+}
+
+// closest = min(closest, dist(c, x)) over the chosen candidate's range  (_kmeans.py:266-270)
+__global__ void __launch_bounds__(kRedThreads)
+pp_update_range_kernel(const double* __restrict__ xs, const int64_t* __restrict__ perm, double c,
+                       int64_t lo, int64_t hi, double* __restrict__ closest) {
+    const double cc = __dmul_rn(c, c);
+    for (int64_t p = lo + (int64_t)blockIdx.x * kRedThreads + threadIdx.x; p < hi;
+         p += (int64_t)gridDim.x * kRedThreads) {
+        const int64_t i = perm[p];
+        closest[i] = fmin(closest[i], sk_sqdist(c, cc, xs[p]));
+    }
 }
 
 // ---- the Lloyd loop: one CTA, everything in shared memory --------------------------------------
@@ -568,8 +754,12 @@ int bind_impl(gr_quantizer* q, const T* X, int64_t rows, int64_t cols, int64_t l
     if (int rc = finish_to_host(q, blocks, 1, 1, &h, st)) return rc;
     q->var = h / (double)N;
 
+    // sorted values and the sort permutation (k-means++ reaches `closest` through it)
+    int64_t* iota = reinterpret_cast<int64_t*>(q->closest);     // free until the next encode
+    iota64_kernel<<<(unsigned)ceil_div<int64_t>(N, 256), 256, 0, st>>>(iota, N);
     size_t need = q->cub_temp_bytes;
-    GR_CUDA_TRY(cub::DeviceRadixSort::SortKeys(q->cub_temp, need, q->x, q->xs, N, 0, 64, st));
+    GR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(q->cub_temp, need, q->x, q->xs, iota, q->perm, N,
+                                                0, 64, st));
     GR_CUDA_TRY(cudaMemsetAsync(q->P, 0, sizeof(double), st));
     need = q->cub_temp_bytes;
     GR_CUDA_TRY(cub::DeviceScan::InclusiveSum(q->cub_temp, need, q->xs, q->P + 1, N, st));
@@ -602,12 +792,6 @@ int64_t choice_uniform(int64_t n, double u) {
         if (run / last > u) return i;
     }
     return n - 1;
-}
-
-template <int TRIALS>
-void launch_eval(gr_quantizer* q, int blocks, cudaStream_t st, const double* cand_x) {
-    pp_eval_kernel<TRIALS><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, q->N, cand_x,
-                                                           q->partial);
 }
 
 template <typename T>
@@ -645,36 +829,72 @@ int encode_impl(gr_quantizer* q, int32_t n_bins, uint32_t seed, int32_t max_iter
     double pot = 0.0;
     if (int rc = finish_to_host(q, blocks, 1, 1, &pot, st)) return rc;
     bool degenerate = false;
+    const int nblk = (int)ceil_div<int64_t>(N, kPpBlock);
+    int64_t* d_lo = q->small_i + 8;
+    int64_t* d_hi = q->small_i + 16;
+    double* d_pot = q->small + 48;
+    std::vector<double> sorted_centres(1, centres[0]);
+    sorted_centres.reserve((size_t)k);
     for (int c = 1; c < k; ++c) {
-        if (!(pot > 0.0)) { degenerate = true; break; }   // every distinct value is a centre already
-        for (int t = 0; t < trials; ++t) h[t] = rs.random_sample() * pot;
+        for (int t = 0; t < trials; ++t) h[t] = rs.random_sample();
         GR_CUDA_TRY(cudaMemcpyAsync(d_rand, h, trials * sizeof(double), cudaMemcpyHostToDevice, st));
-        size_t need = q->cub_temp_bytes;
-        GR_CUDA_TRY(cub::DeviceScan::InclusiveSum(q->cub_temp, need, q->closest, q->cum, N, st));
-        pp_search_kernel<<<1, 32, 0, st>>>(q->cum, q->x, N, d_rand, trials, d_cand_i, d_cand_x);
-        switch (trials) {
-            case 2: launch_eval<2>(q, blocks, st, d_cand_x); break;
-            case 3: launch_eval<3>(q, blocks, st, d_cand_x); break;
-            case 4: launch_eval<4>(q, blocks, st, d_cand_x); break;
-            case 5: launch_eval<5>(q, blocks, st, d_cand_x); break;
-            case 6: launch_eval<6>(q, blocks, st, d_cand_x); break;
-            case 7: launch_eval<7>(q, blocks, st, d_cand_x); break;
-            default: launch_eval<8>(q, blocks, st, d_cand_x); break;
+        GR_CUDA_TRY(cudaMemcpyAsync(q->centres_sorted, sorted_centres.data(),
+                                    sorted_centres.size() * sizeof(double),
+                                    cudaMemcpyHostToDevice, st));
+        pp_block_sums_kernel<<<nblk, kRedThreads, 0, st>>>(q->closest, N, q->bsum);
+        pp_scan_search_kernel<<<1, 1024, 0, st>>>(q->bsum, nblk, q->closest, q->x, q->xs, N, d_rand,
+                                                  trials, q->centres_sorted,
+                                                  (int)sorted_centres.size(), d_cand_i, d_cand_x,
+                                                  d_lo, d_hi, d_pot);
+        // the first centres' ranges are most of the data: stream; later ones: gather the range
+        const bool stream_all = c < kPpStreamRounds;
+        if (stream_all) {
+            switch (trials) {
+                case 2: pp_eval_all_kernel<2><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                case 3: pp_eval_all_kernel<3><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                case 4: pp_eval_all_kernel<4><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                case 5: pp_eval_all_kernel<5><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                case 6: pp_eval_all_kernel<6><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                case 7: pp_eval_all_kernel<7><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+                default: pp_eval_all_kernel<8><<<blocks, kRedThreads, 0, st>>>(q->x, q->closest, N, d_cand_x, q->partial); break;
+            }
+        } else {
+            dim3 eval_grid((unsigned)blocks, (unsigned)trials);
+            pp_eval_range_kernel<<<eval_grid, kRedThreads, 0, st>>>(q->xs, q->perm, q->closest,
+                                                                    d_cand_x, d_lo, d_hi, q->partial);
         }
+        finish_sum_kernel<<<1, 32, 0, st>>>(q->partial, blocks, kMaxTrials, trials, q->small);
         count_launch(4);
         GR_CUDA_TRY(cudaGetLastError());
-        double pots[kMaxTrials], cx[kMaxTrials];
-        finish_sum_kernel<<<1, 32, 0, st>>>(q->partial, blocks, kMaxTrials, trials, q->small);
-        count_launch();
-        GR_CUDA_TRY(cudaMemcpyAsync(pots, q->small, trials * sizeof(double), cudaMemcpyDeviceToHost, st));
-        GR_CUDA_TRY(cudaMemcpyAsync(cx, d_cand_x, trials * sizeof(double), cudaMemcpyDeviceToHost, st));
+        // one copy for the doubles (gains [0..8), candidate values [32..40), pot [48]), one for
+        // the ranges ([8..16) lo, [16..24) hi)
+        double hd[49];
+        int64_t hi64[24];
+        GR_CUDA_TRY(cudaMemcpyAsync(hd, q->small, sizeof(hd), cudaMemcpyDeviceToHost, st));
+        GR_CUDA_TRY(cudaMemcpyAsync(hi64, q->small_i, sizeof(hi64), cudaMemcpyDeviceToHost, st));
         GR_CUDA_TRY(cudaStreamSynchronize(st));
+        const double* gains = hd;
+        const double* cx = hd + 32;
+        const int64_t* lo = hi64 + 8;
+        const int64_t* hi = hi64 + 16;
+        pot = hd[48];
+        if (!(pot > 0.0)) { degenerate = true; break; }   // every distinct value is a centre already
         int best = 0;                                       // np.argmin: first minimum
-        for (int t = 1; t < trials; ++t) if (pots[t] < pots[best]) best = t;
-        pot = pots[best];
+        for (int t = 1; t < trials; ++t)
+            if (pot - gains[t] < pot - gains[best]) best = t;
         centres[(size_t)c] = cx[best];
-        pp_update_kernel<<<blocks, kRedThreads, 0, st>>>(q->x, N, cx[best], q->closest);
-        count_launch();
+        sorted_centres.insert(std::upper_bound(sorted_centres.begin(), sorted_centres.end(), cx[best]),
+                              cx[best]);
+        if (stream_all) {
+            pp_update_all_kernel<<<blocks, kRedThreads, 0, st>>>(q->x, N, cx[best], q->closest);
+            count_launch();
+        } else if (hi[best] > lo[best]) {
+            const int ub = (int)std::min<int64_t>(blocks, ceil_div<int64_t>(hi[best] - lo[best],
+                                                                            kRedThreads));
+            pp_update_range_kernel<<<ub, kRedThreads, 0, st>>>(q->xs, q->perm, cx[best], lo[best],
+                                                              hi[best], q->closest);
+            count_launch();
+        }
     }
 
     if (degenerate) {
@@ -809,8 +1029,8 @@ extern "C" int gr_quantizer_create(gr_quantizer_t** out, int64_t capacity, int d
     q->device = device;
     q->capacity = capacity;
     size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr,
-                                   capacity, 0, 64);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr,
+                                    (const int64_t*)nullptr, (int64_t*)nullptr, capacity, 0, 64);
     cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const double*)nullptr, (double*)nullptr,
                                   capacity);
     q->cub_temp_bytes = std::max(sort_bytes, scan_bytes) + 256;
@@ -821,11 +1041,13 @@ extern "C" int gr_quantizer_create(gr_quantizer_t** out, int64_t capacity, int d
     alloc((void**)&q->xs, nb);
     alloc((void**)&q->P, nb + sizeof(double));
     alloc((void**)&q->closest, nb);
-    alloc((void**)&q->cum, nb);
+    alloc((void**)&q->perm, (size_t)capacity * sizeof(int64_t));
+    alloc((void**)&q->bsum, ((size_t)ceil_div<int64_t>(capacity, kPpBlock) + 1) * sizeof(double));
+    alloc((void**)&q->centres_sorted, kMaxBins * sizeof(double));
     alloc(&q->cub_temp, q->cub_temp_bytes);
     alloc((void**)&q->partial, (size_t)kRedBlocks * kMaxTrials * sizeof(double));
     alloc((void**)&q->small, 64 * sizeof(double));
-    alloc((void**)&q->small_i, 16 * sizeof(int64_t));
+    alloc((void**)&q->small_i, 32 * sizeof(int64_t));
     alloc((void**)&q->lloyd_centers, kMaxBins * sizeof(double));
     alloc((void**)&q->thresholds, kMaxBins * sizeof(double));
     alloc((void**)&q->levels, kMaxBins * sizeof(double));
@@ -848,7 +1070,9 @@ extern "C" int gr_quantizer_destroy(gr_quantizer_t* q) {
     cudaFree(q->xs);
     cudaFree(q->P);
     cudaFree(q->closest);
-    cudaFree(q->cum);
+    cudaFree(q->perm);
+    cudaFree(q->bsum);
+    cudaFree(q->centres_sorted);
     cudaFree(q->cub_temp);
     cudaFree(q->partial);
     cudaFree(q->small);
