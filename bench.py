@@ -869,7 +869,13 @@ def rolx_epilogue_section(X, device, n_roles=8):
                          'GBps_of_X': n * f * 4 / ms / 1e6, 'value': cost}
     del W, H, G8
     torch.cuda.empty_cache()
-    # the grid, on a planted low-rank matrix so that the fits converge like real features do
+    # one-time initialisation of the dense linear-algebra libraries behind torch.linalg (cuSOLVER /
+    # MAGMA handles and workspaces: ~2 s in a fresh process) is not part of the grid
+    t0 = time.perf_counter()
+    from graphrole_b200.roles import factor
+    factor.nndsvda_init(torch.rand(4096, 64, device=device), 4, seed=0)
+    torch.cuda.synchronize()
+    out['linalg_warmup_s'] = time.perf_counter() - t0
     t0 = time.perf_counter()
     grid = DeviceModelGrid.from_device(X)
     grid.timed = True
