@@ -509,7 +509,10 @@ def run_gpu_arm(args):
     # ---- hot path B row-sharded over the ranks (N > 1) -------------------
     if world > 1 and not args.no_nmf:
         torch.cuda.empty_cache()
-        line['nmf_row_sharded'] = nmf_row_sharded_section(device, dist, rank, world)
+        try:      # never lose the headline line to the secondary section
+            line['nmf_row_sharded'] = nmf_row_sharded_section(device, dist, rank, world)
+        except Exception as exc:
+            line['nmf_row_sharded'] = {'error': repr(exc)}
 
     if rank == 0:
         print(json.dumps(line))
