@@ -1,15 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 600 python -m pytest tests -q -m gpu -k "two_gpu" > gpurun_out/r2c35_pytest_two_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2c35_pytest_two_gpu.log
-timeout 600 $TR --master-port 29761 bench.py --gpus 2 > gpurun_out/r2c35_bench_n2.json 2> gpurun_out/r2c35_bench_n2.err; echo "bench rc=$?"
-python - <<'P'
-import json
-try:
-    d = json.loads(open('gpurun_out/r2c35_bench_n2.json').read().strip().splitlines()[-1])
-    print('value', d['value'], 'ms', d['ms_per_step'], 'parity', d.get('parity', {}).get('ok'), d.get('parity', {}).get('bit_identical_to_single_gpu'), 'e2e', d.get('e2e', {}).get('ms_per_step'))
-    print(json.dumps(d.get('nmf_row_sharded'))[:1200])
-except Exception as e:
-    print('bench parse failed', e); print(open('gpurun_out/r2c35_bench_n2.err').read()[-1500:])
+timeout 600 python -m pytest tests/test_prune_level0_gpu.py -q -m gpu -x -k "level0" > gpurun_out/r2c36_pytest_level0.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2c36_pytest_level0.log
+timeout 300 python - > gpurun_out/r2c36_level0.txt 2>&1 <<'P'
+import torch, json, time, sys, os
+sys.path.insert(0, os.getcwd())
+from graphrole_b200.graph.generators import barabasi_albert_csr
+from graphrole_b200.graph import level0
+g = barabasi_albert_csr(10_000_000, 20, seed=0, device='cuda:0')
+for rep in range(4):
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); out = level0.device_features(g); e1.record(); torch.cuda.synchronize()
+    print(json.dumps({'rep': rep, 'level0_ms': round(e0.elapsed_time(e1), 2)}), flush=True)
 P
-timeout 300 $TR --master-port 29771 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/r2c35_bench_ref_n2.json 2> gpurun_out/r2c35_bench_ref_n2.err; echo "ref rc=$?"; cut -c1-200 gpurun_out/r2c35_bench_ref_n2.json
+cat gpurun_out/r2c36_level0.txt | tail -4
