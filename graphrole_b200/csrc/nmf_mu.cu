@@ -551,12 +551,21 @@ static int unpad_factors(gr_nmf* h, float* W, float* H, cudaStream_t st) {
                                 cudaMemcpyDeviceToDevice, st));
     return GR_OK;
 }
+// would the tensor-core kernels take this X at rank r4?  (asked before anything is allocated)
+static bool padded_shape_supported(const gr_nmf* h, const float* X, int64_t ldx) {
+    gr_nmf probe;
+    probe.n = h->n;
+    probe.f = h->f;
+    probe.r = (h->r + 3) & ~3;
+    probe.device = h->device;
+    return nmf_tc_supported(&probe, X, ldx);
+}
 // true when the call should run on the padded handle (which then exists)
 static bool wants_padding(gr_nmf* h, const float* X, int64_t ldx, int* rc) {
     *rc = GR_OK;
     if (h->r % 4 == 0 || getenv("GR_NMF_NO_RANK_PADDING")) return false;
-    if ((*rc = ensure_padded(h)) != GR_OK) return false;
-    return nmf_tc_supported(h->padded, X, ldx);
+    if (!padded_shape_supported(h, X, ldx)) return false;
+    return (*rc = ensure_padded(h)) == GR_OK;
 }
 
 extern "C" int gr_nmf_destroy(gr_nmf_t* h) {
@@ -582,12 +591,7 @@ extern "C" int gr_nmf_takes_tensor_cores(const gr_nmf_t* h, const float* X, int6
     if (!h || !X) return 0;
     if (nmf_tc_supported(h, X, ldx)) return 1;
     if (h->r % 4 == 0 || getenv("GR_NMF_NO_RANK_PADDING")) return 0;
-    gr_nmf probe;               // the shape the padded run would have
-    probe.n = h->n;
-    probe.f = h->f;
-    probe.r = (h->r + 3) & ~3;
-    probe.device = h->device;
-    return nmf_tc_supported(&probe, X, ldx) ? 1 : 0;
+    return padded_shape_supported(h, X, ldx) ? 1 : 0;
 }
 
 extern "C" int gr_nmf_error_f32(gr_nmf_t* h, const float* X, int64_t ldx, const float* W,
