@@ -738,6 +738,31 @@ def nmf_section(device, n=10_000_000, f=512, ranks=(2, 4, 5, 8, 16, 32), iters=1
         del W, H
     out = {'workload': f'X {n}x{f} fp32 U[0,1), shared random init, {iters} iterations',
            'dtype': 'tf32 MMA / fp32 accumulate', 'per_rank': rows}
+    # roofline objects of the two kernels of the path (largest rank timed): algorithmic bytes over
+    # the CUDA-event time of the whole iteration / check, against the measured HBM peak
+    last = rows[-1]
+    r_last = last['r']
+    out['roofline'] = {
+        'iteration': {
+            'kernel': 'nmf_fused_tc_kernel<2> (+ H H^T, partial reduction, H update: 3 small launches)',
+            'bound': 'hbm', 'r': r_last, 'achieved': last['alg_GBps'], 'peak': peak, 'unit': 'GB/s',
+            'frac': last['frac_of_hbm_peak'],
+            'algorithmic_bytes_per_iteration': n * f * 4 + 2 * n * r_last * 4,
+            'traffic': None,
+            'traffic_source': 'profiles/r2_ncu_nmf_tc_raw.csv (n = 4 M, r = 32: dram read 8.77 GB '
+                              'for 8.19 + 0.51 GB algorithmic; not re-measured in this run)',
+            'note': 'co-bound by the SM shared-memory data pipe (DESIGN.md section 6)'},
+        'convergence_check': {
+            'kernel': 'nmf_error_tc_kernel', 'bound': 'hbm', 'r': r_last,
+            'achieved': (n * f * 4 + n * r_last * 4) / last['ms_per_convergence_check'] / 1e6,
+            'peak': peak, 'unit': 'GB/s',
+            'frac': (n * f * 4 + n * r_last * 4) / last['ms_per_convergence_check'] / 1e6 / peak,
+            'algorithmic_bytes_per_check': n * f * 4 + n * r_last * 4,
+            'traffic': None,
+            'traffic_source': 'profiles/r2_ncu_nmf_error_tc_raw.csv (n = 4 M, r = 32: dram read '
+                              '8.71 GB for 8.70 GB algorithmic at 6.83 TB/s)',
+            'note': 'read-only stream: above the copy peak of MEASURED_PEAKS.json; the time '
+                    'includes the D2H of the partials and the stream synchronisation'}}
     try:
         out['rolx_epilogue'] = rolx_epilogue_section(X, device)
     except Exception as exc:
