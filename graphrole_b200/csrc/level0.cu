@@ -205,8 +205,17 @@ __device__ __forceinline__ bool precedes(int64_t du, int32_t u, int64_t dv, int3
     return du < dv || (du == dv && u < v);
 }
 
+// degrees as 32-bit words: the orientation looks up the degree of every neighbour (nnz random
+// reads); 4 n bytes stay in L2 where the two 8-byte row pointers of an 8 (n + 1)-byte array do not
+__global__ void degree_kernel(int64_t n, const int64_t* __restrict__ rowptr,
+                              int32_t* __restrict__ deg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) deg[i] = (int32_t)(rowptr[i + 1] - rowptr[i]);
+}
+
 __global__ void orient_count_kernel(int64_t n, const int64_t* __restrict__ rowptr,
                                     const int32_t* __restrict__ colidx,
+                                    const int32_t* __restrict__ deg,
                                     int32_t* __restrict__ out_count,
                                     unsigned long long* __restrict__ nbr_deg_sum) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +228,7 @@ __global__ void orient_count_kernel(int64_t n, const int64_t* __restrict__ rowpt
     unsigned long long dsum = 0;
     for (int64_t k = a + sub; k < b; k += kLanes) {
         const int32_t v = colidx[k];
-        const int64_t dv = rowptr[v + 1] - rowptr[v];
+        const int64_t dv = deg[v];
         dsum += (unsigned long long)dv;
         cnt += precedes(di, (int32_t)i, dv, v) ? 1 : 0;
     }
@@ -237,6 +246,7 @@ __global__ void orient_count_kernel(int64_t n, const int64_t* __restrict__ rowpt
 // one thread per row: copy the kept arcs in order (rows are ascending, so the oriented rows are too)
 __global__ void orient_fill_kernel(int64_t n, const int64_t* __restrict__ rowptr,
                                    const int32_t* __restrict__ colidx,
+                                   const int32_t* __restrict__ deg,
                                    const int64_t* __restrict__ optr, int32_t* __restrict__ ocol) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = gid / kLanes;
@@ -252,7 +262,7 @@ __global__ void orient_fill_kernel(int64_t n, const int64_t* __restrict__ rowptr
         int32_t v = 0;
         if (k < b) {
             v = colidx[k];
-            keep = precedes(di, (int32_t)i, rowptr[v + 1] - rowptr[v], v);
+            keep = precedes(di, (int32_t)i, deg[v], v);
         }
         // only the row's own 8 lanes vote: the other groups of the warp have other trip counts
         const unsigned m = __ballot_sync(group_mask, keep) & group_mask;
@@ -262,22 +272,57 @@ __global__ void orient_fill_kernel(int64_t n, const int64_t* __restrict__ rowptr
     }
 }
 
-// 8-lane group per row u: for every v in N+(u) intersect N+(u) and N+(v)
-__global__ void triangle_kernel(int64_t n, const int64_t* __restrict__ optr,
-                                const int32_t* __restrict__ ocol,
-                                unsigned long long* __restrict__ tri) {
+// 8-lane group per row u: for every v in N+(u) intersect N+(u) and N+(v).
+// N+(u) of up to kHashMax arcs (every row of a preferential-attachment graph: a node keeps the
+// arcs to its higher-degree neighbours) goes into a 64-slot open-addressing table in shared
+// memory; the lanes then stream N+(v) -- coalesced -- and probe the table: one or two
+// shared-memory reads per element instead of a binary search of ~log2|N+| dependent loads.
+// Longer rows, and neighbours whose list is much longer than u's, keep the binary search over
+// the shorter list.
+constexpr int kHashSlots = 64, kHashMax = 40;
+__device__ __forceinline__ int hash_slot(int32_t w) {
+    return (int)(((uint32_t)w * 2654435761u) >> 26);          // 6 bits
+}
+
+__global__ void __launch_bounds__(256)
+triangle_kernel(int64_t n, const int64_t* __restrict__ optr, const int32_t* __restrict__ ocol,
+                unsigned long long* __restrict__ tri) {
+    __shared__ int32_t table[256 / kLanes][kHashSlots];
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t u = gid / kLanes;
     const int sub = (int)(gid % kLanes);
-    if (u >= n) return;
+    const int grp = threadIdx.x / kLanes;
+    if (u >= n) return;                            // whole groups leave together
+    const unsigned group_mask = 0xffu << ((threadIdx.x & 31) / kLanes * kLanes);
     const int64_t ua = optr[u], ub = optr[u + 1];
+    const bool hashed = ub > ua && ub - ua <= kHashMax;
+    if (hashed) {
+        for (int s = sub; s < kHashSlots; s += kLanes) table[grp][s] = -1;
+        __syncwarp(group_mask);
+        for (int64_t q = ua + sub; q < ub; q += kLanes) {
+            const int32_t w = ocol[q];
+            int h = hash_slot(w);
+            while (atomicCAS(&table[grp][h], -1, w) != -1) h = (h + 1) & (kHashSlots - 1);
+        }
+        __syncwarp(group_mask);
+    }
     unsigned long long mine = 0;                   // triangles credited to u by this lane
     for (int64_t k = ua; k < ub; ++k) {
         const int32_t v = ocol[k];
         const int64_t va = optr[v], vb = optr[v + 1];
         unsigned long long found = 0;              // credited to v by this lane
-        // rows are sorted by node id, not by the orientation order: search the whole other row
-        if (vb - va <= ub - ua) {
+        if (hashed && vb - va <= 4 * (ub - ua)) {
+            for (int64_t q = va + sub; q < vb; q += kLanes) {
+                const int32_t w = ocol[q];
+                int h = hash_slot(w);
+                int32_t t;
+                while ((t = table[grp][h]) != -1) {
+                    if (t == w) { ++found; atomicAdd(tri + w, 1ull); break; }
+                    h = (h + 1) & (kHashSlots - 1);
+                }
+            }
+        } else if (vb - va <= ub - ua) {
+            // rows are sorted by node id, not by the orientation order: search the whole other row
             for (int64_t q = va + sub; q < vb; q += kLanes) {
                 const int32_t w = ocol[q];
                 const int64_t p = find(ocol, ua, ub, w);
@@ -328,7 +373,7 @@ int level0_triangles(int64_t n, int64_t nnz, const int64_t* rowptr, const int32_
     const unsigned blocks_n = (unsigned)ceil_div<int64_t>(n, 256);
     const unsigned blocks_g = (unsigned)ceil_div<int64_t>(n * kLanes, 256);
     // workspace: flag | counts (int32 n + 1) | optr (int64 n + 1) | nbr_deg_sum (u64 n) |
-    // tri (u64 n) | ocol (int32 nnz: every arc is kept at most once) | cub temp
+    // tri (u64 n) | ocol (int32 nnz: every arc is kept at most once) | deg (int32 n) | cub temp
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int64_t*)nullptr,
                                   n + 1);
@@ -337,7 +382,8 @@ int level0_triangles(int64_t n, int64_t nnz, const int64_t* rowptr, const int32_
                  o_dsum = o_optr + ((size_t)(n + 1) * 8 + 255) / 256 * 256,
                  o_tri = o_dsum + ((size_t)n * 8 + 255) / 256 * 256,
                  o_ocol = o_tri + ((size_t)n * 8 + 255) / 256 * 256,
-                 o_tmp = o_ocol + ((size_t)nnz * 4 + 255) / 256 * 256,
+                 o_deg = o_ocol + ((size_t)nnz * 4 + 255) / 256 * 256,
+                 o_tmp = o_deg + ((size_t)n * 4 + 255) / 256 * 256,
                  total = o_tmp + scan_bytes + 256;
     GR_CUDA_TRY(cudaMallocAsync((void**)&ws, total, st));
     int* flag = reinterpret_cast<int*>(ws + o_flag);
@@ -346,6 +392,7 @@ int level0_triangles(int64_t n, int64_t nnz, const int64_t* rowptr, const int32_
     unsigned long long* dsum = reinterpret_cast<unsigned long long*>(ws + o_dsum);
     unsigned long long* tri = reinterpret_cast<unsigned long long*>(ws + o_tri);
     int32_t* ocol = reinterpret_cast<int32_t*>(ws + o_ocol);
+    int32_t* deg = reinterpret_cast<int32_t*>(ws + o_deg);
     cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
     any_self_loop_kernel<<<blocks_n, 256, 0, st>>>(n, rowptr, colidx, flag);
     int h_flag = 0;
@@ -359,14 +406,15 @@ int level0_triangles(int64_t n, int64_t nnz, const int64_t* rowptr, const int32_
     }
     cudaMemsetAsync(cnt + n, 0, sizeof(int32_t), st);
     cudaMemsetAsync(tri, 0, (size_t)n * sizeof(unsigned long long), st);
-    orient_count_kernel<<<blocks_g, 256, 0, st>>>(n, rowptr, colidx, cnt, dsum);
+    degree_kernel<<<blocks_n, 256, 0, st>>>(n, rowptr, deg);
+    orient_count_kernel<<<blocks_g, 256, 0, st>>>(n, rowptr, colidx, deg, cnt, dsum);
     size_t tmp = scan_bytes;
     e = cub::DeviceScan::ExclusiveSum(ws + o_tmp, tmp, cnt, optr, n + 1, st);
-    orient_fill_kernel<<<blocks_g, 256, 0, st>>>(n, rowptr, colidx, optr, ocol);
+    orient_fill_kernel<<<blocks_g, 256, 0, st>>>(n, rowptr, colidx, deg, optr, ocol);
     triangle_kernel<<<blocks_g, 256, 0, st>>>(n, optr, ocol, tri);
     triangle_finish_kernel<<<blocks_n, 256, 0, st>>>(n, rowptr, tri, dsum, out_w, diag, internal,
                                                      external);
-    count_launch(5);
+    count_launch(6);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFreeAsync(ws, st);
     if (e != cudaSuccess) return fail(GR_ERR_CUDA, "level-0 triangle path: %s", cudaGetErrorString(e));
