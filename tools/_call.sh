@@ -1,20 +1,24 @@
 #!/bin/bash
+# round-end validation on one B200: GPU test suite, smoke, the default bench, and an ncu capture
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_prune_level0_gpu.py -q -m gpu -x > gpurun_out/r2c39_pytest_level0.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2c39_pytest_level0.log
-timeout 300 python - > gpurun_out/r2c39_level0.txt 2>&1 <<'P'
-import torch, json, time, sys, os
-sys.path.insert(0, os.getcwd())
-from graphrole_b200.graph.generators import barabasi_albert_csr, erdos_renyi_csr
-from graphrole_b200.graph import level0
-for name, g in (('BA 10M m=20', barabasi_albert_csr(10_000_000, 20, seed=0, device='cuda:0')),
-                ('ER 1M 20M edges', erdos_renyi_csr(1_000_000, 20_000_000, seed=0, device='cuda:0'))):
-    for env in ('', '1'):
-        ts = []
-        for rep in range(4):
-            torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); out = level0.device_features(g); e1.record(); torch.cuda.synchronize()
-            ts.append(round(e0.elapsed_time(e1), 2))
-        print(json.dumps({'graph': name, 'level0_ms': ts}), flush=True)
-        break
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r2c40_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2c40_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2c40_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2c40_smoke.log
+( time timeout 900 python bench.py > gpurun_out/r2c40_bench_n1.json 2> gpurun_out/r2c40_bench_n1.err ) 2> gpurun_out/r2c40_bench_n1.time; echo "bench rc=$?"; tail -3 gpurun_out/r2c40_bench_n1.time
+python - <<'P'
+import json
+d = json.loads(open('gpurun_out/r2c40_bench_n1.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'parity', d['parity']['ok'], 'e2e', d['e2e']['ms_per_step'], 'launches', d['gpu_launches'])
+print('next', {k: (v.get('ms') or v.get('wall_s')) for k, v in d['next'].items()}, d['next']['extract_features_device_resident'].get('kernel_ms'))
+print('nmf parity', d['nmf'].get('parity', {}).get('ok'), 'roofline', {k: round(v['frac'], 3) for k, v in d['nmf'].get('roofline', {}).items()})
+g = d['nmf']['rolx_epilogue']
+print('grid', g.get('model_selection_grid'), 'warmup', g.get('linalg_warmup_s'))
 P
-cat gpurun_out/r2c39_level0.txt | tail -4
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:triangle_kernel -c 1 -o gpurun_out/r2c40_ncu_triangle -f python - > gpurun_out/r2c40_ncu.log 2>&1 <<'P'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from graphrole_b200.graph.generators import barabasi_albert_csr
+from graphrole_b200.graph import level0
+g = barabasi_albert_csr(4_000_000, 20, seed=0, device='cuda:0')
+level0.device_features(g)
+P
+echo "ncu rc=$?"
