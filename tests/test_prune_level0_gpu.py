@@ -334,8 +334,26 @@ def test_level0_triangle_fast_path_equals_general_kernels(refex_cases, monkeypat
         cols = level0.device_features(g, DEV)
         for col in ref.columns:
             np.testing.assert_array_equal(cols[col].cpu().numpy(), ref[col].values, err_msg=col)
+    # the intersection has three forms (shared-memory hash table of N+(u) for rows of up to 40
+    # oriented arcs, binary search over the shorter list beyond that, and -- hashed row, much
+    # longer neighbour list -- binary search in the neighbour's list): a dense graph (oriented rows
+    # of ~100 arcs) and a clique with a sparse periphery (short rows whose neighbours are clique
+    # members with ~100 oriented arcs) reach the two that sparse graphs do not
+    rng = np.random.RandomState(5)
+    clique = 150
+    cu, cv = np.triu_indices(clique, k=1)
+    per = np.arange(clique, clique + 6000)
+    pu = np.repeat(per, 3)
+    pv = rng.randint(0, clique, size=pu.size)
+    qu = per
+    qv = rng.permutation(per)
+    keep = qu != qv
+    mixed = CSRGraph.from_edges(np.concatenate([cu, pu, qu[keep]]),
+                                np.concatenate([cv, pv, qv[keep]]), n=clique + 6000)
     graphs = [erdos_renyi_csr(50_000, 400_000, seed=1, device=DEV),
               barabasi_albert_csr(60_000, 9, seed=2, device=DEV),
+              erdos_renyi_csr(3_000, 300_000, seed=3, device=DEV),
+              mixed,
               CSRGraph.from_edges([0, 1, 5], [1, 2, 6], n=9)]        # isolated nodes 3, 4, 7, 8
     for g in graphs:
         fast = level0.device_features(g, DEV)

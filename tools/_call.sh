@@ -1,7 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-: > gpurun_out/r2c42_level0_variants.txt
-for cfg in 8 8p 4 4p 16 16p; do
-  GR_LEVEL0_TRI=$cfg timeout 200 python tools/exp_level0_variants.py 2>&1 | tail -2 >> gpurun_out/r2c42_level0_variants.txt
-done
-cat gpurun_out/r2c42_level0_variants.txt
+timeout 600 python -m pytest tests/test_prune_level0_gpu.py -q -m gpu -x -k "triangle or level0" > gpurun_out/r2c43_pytest_level0.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2c43_pytest_level0.log
