@@ -1,3 +1,8 @@
 #!/bin/bash
+# scratch: the command list of the most recent gpurun call (overwritten per call); the round-end
+# validation of the third session was
+#   python -m pytest tests -x -q -m gpu; python -c "import __graft_entry__ as g; g.smoke()"; python bench.py
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_prune_level0_gpu.py -q -m gpu -x -k "triangle or level0" > gpurun_out/r2c43_pytest_level0.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2c43_pytest_level0.log
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
