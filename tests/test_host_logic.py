@@ -373,3 +373,20 @@ def test_orthonormal_basis_cholesky_qr2_and_householder_fallback():
     assert float((Q.T @ Q - torch.eye(18, dtype=torch.float64)).abs().max()) < 1e-6
     B5 = torch.linalg.qr(A5.double())[0]
     assert float((Q @ (Q.T @ B5) - B5).abs().max()) < 1e-4
+
+
+def test_nndsvda_init_on_a_tall_matrix_matches_sklearn_cpu():
+    """roles.factor.nndsvda_init is device-agnostic torch code: on CPU tensors a tall matrix takes
+    the CholeskyQR2 sketches (6000 rows >= 64 x 14 columns) and must give sklearn's start for the
+    same NumPy random stream (sklearn/decomposition/_nmf.py:214-366)."""
+    import torch
+    sk = pytest.importorskip('sklearn.decomposition._nmf')
+    rng = np.random.RandomState(1)
+    X = (rng.rand(6000, 5) ** 2 * np.array([9.0, 5.0, 3.0, 2.0, 1.0])) @ rng.rand(5, 40) + \
+        0.01 * rng.rand(6000, 40)
+    np.random.seed(7)
+    W_ref, H_ref = sk._initialize_nmf(X, 4, init='nndsvda')
+    np.random.seed(7)
+    W, H = factor.nndsvda_init(torch.from_numpy(X), 4)
+    np.testing.assert_allclose(W.numpy(), W_ref, rtol=5e-4, atol=2e-5)
+    np.testing.assert_allclose(H.numpy(), H_ref, rtol=5e-4, atol=2e-5)
