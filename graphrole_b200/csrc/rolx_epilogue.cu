@@ -131,6 +131,42 @@ center_kernel(const T* __restrict__ src, int64_t N, int64_t cols, int64_t ld, do
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
+// ---- the data mean as NumPy computes it ------------------------------------------------------
+// sklearn centres the data by X.mean(axis=0) (_kmeans.py:1486-1490), i.e. NumPy's pairwise sum
+// (numpy/_core/src/umath/loops_utils.h.src: blocks of <= 128 values summed with eight running
+// accumulators, halves split at a multiple of 8 and added pairwise).  On grid-valued data the
+// k-means++ seeds are grid values, their midpoints are data values, and which centre such an
+// exactly-equidistant point joins falls with the LAST BIT of that mean (measured: centres 1e-3
+// apart after the first Lloyd step with a mean from an ordinary parallel reduction).  So the mean
+// is summed in NumPy's order: one thread per leaf block here, the pairwise tree on the host.
+template <typename T>
+__global__ void __launch_bounds__(128)
+numpy_leaf_sums_kernel(const T* __restrict__ src, int64_t cols, int64_t ld,
+                       const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
+                       int64_t n_leaves, double* __restrict__ out) {
+    const int64_t leaf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    const int64_t off = offs[leaf];
+    const int n = lens[leaf];
+    if (n < 8) {
+        double r = 0.0;
+        for (int j = 0; j < n; ++j) r = __dadd_rn(r, load_value(src, off + j, cols, ld));
+        out[leaf] = r;
+        return;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = load_value(src, off + j, cols, ld);
+    const int m = n - (n % 8);
+    for (int i = 8; i < m; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], load_value(src, off + i + j, cols, ld));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (int j = m; j < n; ++j) res = __dadd_rn(res, load_value(src, off + j, cols, ld));
+    out[leaf] = res;
+}
+
 // stage 2: out[t] = sum over blocks of partial[b * stride + t], fixed order
 __global__ void finish_sum_kernel(const double* __restrict__ partial, int blocks, int stride,
                                   int count, double* __restrict__ out) {
@@ -730,6 +766,59 @@ int finish_to_host(gr_quantizer* q, int blocks, int stride, int count, double* h
     return GR_OK;
 }
 
+// NumPy's pairwise sum (see numpy_leaf_sums_kernel): the leaves of its recursion ...
+void numpy_leaves(int64_t off, int64_t n, std::vector<int64_t>& offs, std::vector<int32_t>& lens) {
+    if (n <= 128) {
+        offs.push_back(off);
+        lens.push_back((int32_t)n);
+        return;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    numpy_leaves(off, n2, offs, lens);
+    numpy_leaves(off + n2, n - n2, offs, lens);
+}
+// ... and its additions over the leaf sums, in the same order
+double numpy_combine(const double* leaf, int64_t& next, int64_t n) {
+    if (n <= 128) return leaf[next++];
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    const double a = numpy_combine(leaf, next, n2);
+    const double b = numpy_combine(leaf, next, n - n2);
+    return a + b;
+}
+template <typename T>
+int numpy_sum(const T* X, int64_t N, int64_t cols, int64_t ld, double* out, cudaStream_t st) {
+    std::vector<int64_t> offs;
+    std::vector<int32_t> lens;
+    offs.reserve((size_t)(N / 64 + 2));
+    lens.reserve((size_t)(N / 64 + 2));
+    numpy_leaves(0, N, offs, lens);
+    const int64_t n_leaves = (int64_t)offs.size();
+    char* ws = nullptr;
+    const size_t b_off = (size_t)n_leaves * 8, b_len = ((size_t)n_leaves * 4 + 7) / 8 * 8;
+    GR_CUDA_TRY(cudaMallocAsync((void**)&ws, 2 * b_off + b_len, st));
+    int64_t* d_offs = reinterpret_cast<int64_t*>(ws);
+    double* d_out = reinterpret_cast<double*>(ws + b_off);
+    int32_t* d_lens = reinterpret_cast<int32_t*>(ws + 2 * b_off);
+    cudaError_t e = cudaMemcpyAsync(d_offs, offs.data(), b_off, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_lens, lens.data(), (size_t)n_leaves * 4, cudaMemcpyHostToDevice, st);
+    numpy_leaf_sums_kernel<T><<<(unsigned)ceil_div<int64_t>(n_leaves, 128), 128, 0, st>>>(
+        X, cols, ld, d_offs, d_lens, n_leaves, d_out);
+    count_launch();
+    std::vector<double> leaf((size_t)n_leaves);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(leaf.data(), d_out, b_off, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) return fail(GR_ERR_CUDA, "gr_quantizer_bind (mean): %s", cudaGetErrorString(e));
+    int64_t next = 0;
+    *out = numpy_combine(leaf.data(), next, N);
+    return GR_OK;
+}
+
 template <typename T>
 int bind_impl(gr_quantizer* q, const T* X, int64_t rows, int64_t cols, int64_t ld, void* stream) {
     GR_REQUIRE(q != nullptr, "gr_quantizer_bind: handle is NULL");
@@ -745,9 +834,7 @@ int bind_impl(gr_quantizer* q, const T* X, int64_t rows, int64_t cols, int64_t l
     const int blocks = reduce_blocks(N);
 
     double h = 0.0;
-    sum_kernel<T><<<blocks, kRedThreads, 0, st>>>(X, N, cols, ld, q->partial);
-    count_launch();
-    if (int rc = finish_to_host(q, blocks, 1, 1, &h, st)) return rc;
+    if (int rc = numpy_sum(X, N, cols, ld, &h, st)) return rc;
     q->mean = h / (double)N;
     center_kernel<T><<<blocks, kRedThreads, 0, st>>>(X, N, cols, ld, q->mean, q->x, q->partial);
     count_launch();

@@ -69,7 +69,7 @@ def test_encode_equals_sklearn_kmeans_beyond_fixture_sizes(n, k):
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize('kind', ['near_duplicates', 'ties', 'heavy_zero_mass'])
+@pytest.mark.parametrize('kind', ['near_duplicates', 'ties', 'heavy_zero_mass', 'grid'])
 def test_seeding_ranges_on_awkward_data(kind):
     """The k-means++ seeding evaluates a candidate only on the sorted range between the chosen
     centres next to it (csrc/rolx_epilogue.cu).  Data that stress that rule: values within
@@ -77,22 +77,24 @@ def test_seeding_ranges_on_awkward_data(kind):
     whole range), ties (a candidate equal to a chosen centre takes none) and a large mass of
     equal values -- against the NumPy restatement of scikit-learn's KMeans, 32 and 64 bins (the
     range form starts with the 20th centre).
-    The tied values are drawn from a pool of 1000 random reals, not from a grid: on grid-valued
-    data (e.g. round(x, 3)) the k-means++ seeds are grid values, their midpoints are data values,
-    and scikit-learn assigns those exactly-equidistant points by the last bit of the data mean
-    (NumPy's pairwise sum) -- measured here: same seeds as the oracle, centres 1e-3 apart after
-    the first Lloyd step, with this kernel and with the round-2 one alike.  That is the
-    "unstable target" regime DESIGN.md section 7 excludes, not a property of the seeding."""
+    'grid': values rounded to three decimals.  There the k-means++ seeds are grid values, their
+    midpoints are data values, and scikit-learn assigns those exactly-equidistant points by the
+    last bit of the data mean -- with a mean from an ordinary parallel reduction the centres were
+    1e-3 off after the first Lloyd step (same seeds).  The library therefore sums the mean in
+    NumPy's pairwise order (numpy_leaf_sums_kernel + the tree on the host), which makes this
+    case equal too."""
     rng = np.random.RandomState(11)
     n = 20_000
     if kind == 'near_duplicates':
         X = np.concatenate([0.5 + 1e-9 * rng.rand(n // 2), rng.rand(n - n // 2)])
     elif kind == 'ties':
         X = (rng.rand(1000) ** 2)[rng.randint(0, 1000, size=n)]
+    elif kind == 'grid':
+        X = np.round(rng.rand(n) ** 2, 3)
     else:
         X = np.abs(rng.randn(n)) * (rng.rand(n) < 0.3)
     X = rng.permutation(X).reshape(-1, 4)
-    for k in (32, 64):
+    for k in ((8, 32, 64) if kind == 'grid' else (32, 64)):
         np.testing.assert_allclose(factor.encode(X, k), oracle.encode(X, k), rtol=1e-9, atol=1e-12)
 
 

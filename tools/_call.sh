@@ -1,8 +1,3 @@
 #!/bin/bash
-# scratch: the command list of the most recent gpurun call (overwritten per call); the round-end
-# validation of the third session was
-#   python -m pytest tests -x -q -m gpu; python -c "import __graft_entry__ as g; g.smoke()"; python bench.py
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
+timeout 600 python -m pytest tests/test_rolx_gpu.py -q -m gpu > gpurun_out/r2c48_pytest_rolx.log 2>&1; echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|Mismatched" gpurun_out/r2c48_pytest_rolx.log | head -12
