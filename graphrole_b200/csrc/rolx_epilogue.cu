@@ -69,6 +69,13 @@ struct gr_quantizer {
     int64_t* perm = nullptr;    // sorted position -> original position
     double* bsum = nullptr;     // k-means++: (cumulative) sums of `closest` per kPpBlock entries
     double* centres_sorted = nullptr;  // [kMaxBins] chosen centres, ascending
+    // NumPy-ordered mean: the leaf table of its pairwise recursion for np_N entries (kept across
+    // binds of equally sized matrices) and the leaf sums
+    int64_t np_N = 0, np_leaves = 0;
+    int64_t* np_offs = nullptr;
+    int32_t* np_lens = nullptr;
+    double* np_out = nullptr;
+    std::vector<double> np_host;
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
     double* partial = nullptr;  // [kRedBlocks * kMaxTrials]
@@ -140,31 +147,39 @@ center_kernel(const T* __restrict__ src, int64_t N, int64_t cols, int64_t ld, do
 // apart after the first Lloyd step with a mean from an ordinary parallel reduction).  So the mean
 // is summed in NumPy's order: one thread per leaf block here, the pairwise tree on the host.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 numpy_leaf_sums_kernel(const T* __restrict__ src, int64_t cols, int64_t ld,
                        const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
                        int64_t n_leaves, double* __restrict__ out) {
-    const int64_t leaf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= n_leaves) return;
+    // eight lanes per leaf = NumPy's eight accumulators: lane j sums a[j], a[8 + j], a[16 + j], ...
+    // in that order (64 contiguous bytes per step and leaf), then the fixed pairing
+    // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)) by xor shuffles (a + b == b + a bit for
+    // bit, so every lane of a pair holds the same partial), then the tail on lane 0.
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t leaf = gid >> 3;
+    const int j = (int)(gid & 7);
+    if (leaf >= n_leaves) return;                 // whole 8-lane groups leave together
+    const unsigned group_mask = 0xffu << ((threadIdx.x & 31) & ~7);
     const int64_t off = offs[leaf];
     const int n = lens[leaf];
     if (n < 8) {
-        double r = 0.0;
-        for (int j = 0; j < n; ++j) r = __dadd_rn(r, load_value(src, off + j, cols, ld));
-        out[leaf] = r;
+        if (j == 0) {
+            double r = 0.0;
+            for (int i = 0; i < n; ++i) r = __dadd_rn(r, load_value(src, off + i, cols, ld));
+            out[leaf] = r;
+        }
         return;
     }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = load_value(src, off + j, cols, ld);
+    double r = load_value(src, off + j, cols, ld);
     const int m = n - (n % 8);
-    for (int i = 8; i < m; i += 8)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], load_value(src, off + i + j, cols, ld));
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (int j = m; j < n; ++j) res = __dadd_rn(res, load_value(src, off + j, cols, ld));
-    out[leaf] = res;
+    for (int i = 8; i < m; i += 8) r = __dadd_rn(r, load_value(src, off + i + j, cols, ld));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1, 8));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2, 8));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4, 8));
+    if (j == 0) {
+        for (int i = m; i < n; ++i) r = __dadd_rn(r, load_value(src, off + i, cols, ld));
+        out[leaf] = r;
+    }
 }
 
 // stage 2: out[t] = sum over blocks of partial[b * stride + t], fixed order
@@ -788,34 +803,44 @@ double numpy_combine(const double* leaf, int64_t& next, int64_t n) {
     return a + b;
 }
 template <typename T>
-int numpy_sum(const T* X, int64_t N, int64_t cols, int64_t ld, double* out, cudaStream_t st) {
-    std::vector<int64_t> offs;
-    std::vector<int32_t> lens;
-    offs.reserve((size_t)(N / 64 + 2));
-    lens.reserve((size_t)(N / 64 + 2));
-    numpy_leaves(0, N, offs, lens);
-    const int64_t n_leaves = (int64_t)offs.size();
-    char* ws = nullptr;
-    const size_t b_off = (size_t)n_leaves * 8, b_len = ((size_t)n_leaves * 4 + 7) / 8 * 8;
-    GR_CUDA_TRY(cudaMallocAsync((void**)&ws, 2 * b_off + b_len, st));
-    int64_t* d_offs = reinterpret_cast<int64_t*>(ws);
-    double* d_out = reinterpret_cast<double*>(ws + b_off);
-    int32_t* d_lens = reinterpret_cast<int32_t*>(ws + 2 * b_off);
-    cudaError_t e = cudaMemcpyAsync(d_offs, offs.data(), b_off, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_lens, lens.data(), (size_t)n_leaves * 4, cudaMemcpyHostToDevice, st);
-    numpy_leaf_sums_kernel<T><<<(unsigned)ceil_div<int64_t>(n_leaves, 128), 128, 0, st>>>(
-        X, cols, ld, d_offs, d_lens, n_leaves, d_out);
+int numpy_sum(gr_quantizer* q, const T* X, int64_t N, int64_t cols, int64_t ld, double* out,
+              cudaStream_t st) {
+    if (q->np_N != N) {
+        std::vector<int64_t> offs;
+        std::vector<int32_t> lens;
+        offs.reserve((size_t)(N / 64 + 2));
+        lens.reserve((size_t)(N / 64 + 2));
+        numpy_leaves(0, N, offs, lens);
+        cudaFree(q->np_offs);
+        cudaFree(q->np_lens);
+        cudaFree(q->np_out);
+        q->np_offs = nullptr;
+        q->np_lens = nullptr;
+        q->np_out = nullptr;
+        q->np_N = 0;
+        const size_t nl = offs.size();
+        GR_CUDA_TRY(cudaMalloc((void**)&q->np_offs, nl * sizeof(int64_t)));
+        GR_CUDA_TRY(cudaMalloc((void**)&q->np_lens, nl * sizeof(int32_t)));
+        GR_CUDA_TRY(cudaMalloc((void**)&q->np_out, nl * sizeof(double)));
+        GR_CUDA_TRY(cudaMemcpyAsync(q->np_offs, offs.data(), nl * sizeof(int64_t),
+                                    cudaMemcpyHostToDevice, st));
+        GR_CUDA_TRY(cudaMemcpyAsync(q->np_lens, lens.data(), nl * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, st));
+        GR_CUDA_TRY(cudaStreamSynchronize(st));      // the host vectors go out of scope
+        q->np_leaves = (int64_t)nl;
+        q->np_host.resize(nl);
+        q->np_N = N;
+    }
+    const int64_t n_leaves = q->np_leaves;
+    numpy_leaf_sums_kernel<T><<<(unsigned)ceil_div<int64_t>(n_leaves * 8, 256), 256, 0, st>>>(
+        X, cols, ld, q->np_offs, q->np_lens, n_leaves, q->np_out);
     count_launch();
-    std::vector<double> leaf((size_t)n_leaves);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(leaf.data(), d_out, b_off, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFreeAsync(ws, st);
-    if (e != cudaSuccess) return fail(GR_ERR_CUDA, "gr_quantizer_bind (mean): %s", cudaGetErrorString(e));
+    GR_CUDA_TRY(cudaGetLastError());
+    GR_CUDA_TRY(cudaMemcpyAsync(q->np_host.data(), q->np_out, (size_t)n_leaves * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    GR_CUDA_TRY(cudaStreamSynchronize(st));
     int64_t next = 0;
-    *out = numpy_combine(leaf.data(), next, N);
+    *out = numpy_combine(q->np_host.data(), next, N);
     return GR_OK;
 }
 
@@ -834,7 +859,7 @@ int bind_impl(gr_quantizer* q, const T* X, int64_t rows, int64_t cols, int64_t l
     const int blocks = reduce_blocks(N);
 
     double h = 0.0;
-    if (int rc = numpy_sum(X, N, cols, ld, &h, st)) return rc;
+    if (int rc = numpy_sum(q, X, N, cols, ld, &h, st)) return rc;
     q->mean = h / (double)N;
     center_kernel<T><<<blocks, kRedThreads, 0, st>>>(X, N, cols, ld, q->mean, q->x, q->partial);
     count_launch();
@@ -1160,6 +1185,9 @@ extern "C" int gr_quantizer_destroy(gr_quantizer_t* q) {
     cudaFree(q->perm);
     cudaFree(q->bsum);
     cudaFree(q->centres_sorted);
+    cudaFree(q->np_offs);
+    cudaFree(q->np_lens);
+    cudaFree(q->np_out);
     cudaFree(q->cub_temp);
     cudaFree(q->partial);
     cudaFree(q->small);
