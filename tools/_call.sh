@@ -1,3 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_rolx_gpu.py -q -m gpu -x -k "seeding or golden or one_bind or float32_storage or strided" > gpurun_out/r2c50_pytest_rolx.log 2>&1; echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|Mismatched" gpurun_out/r2c50_pytest_rolx.log | head -8
+timeout 60 python tools/bench_encode.py > gpurun_out/r2c51_bench_encode.txt 2>&1; head -3 gpurun_out/r2c51_bench_encode.txt | cut -c1-200; python - <<'P'
+import torch, time, sys, os
+sys.path.insert(0, os.getcwd())
+from graphrole_b200 import _native
+W = torch.rand(10_000_000, 8, device='cuda:0') ** 2
+q = _native.Quantizer(W.numel(), 'cuda:0')
+q.bind(W); torch.cuda.synchronize()
+t0 = time.perf_counter(); q.bind(W); torch.cuda.synchronize(); print('second bind ms', round((time.perf_counter() - t0) * 1e3, 2))
+P
