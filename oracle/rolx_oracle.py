@@ -95,6 +95,36 @@ def lloyd_1d(x, centers, tol, max_iter=300):
     return labels, centers, it + 1
 
 
+def numpy_pairwise_sum(a):
+    """np.add.reduce of a contiguous float64 vector, restated (numpy/_core/src/umath/
+    loops_utils.h.src, pairwise sum): blocks of <= 128 values with eight running accumulators
+    combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail; longer inputs are
+    split at n/2 rounded down to a multiple of 8 and the halves added.  The quantiser's bind sums
+    the data mean in exactly this order (csrc/rolx_epilogue.cu: numpy_leaf_sums_kernel +
+    numpy_combine) because on grid-valued data scikit-learn's assignment of exactly-equidistant
+    points falls with the last bit of X.mean(); tests/test_oracle_rolx.py pins this restatement
+    to the installed NumPy bit for bit."""
+    a = np.asarray(a, dtype=np.float64)
+    n = a.size
+    if n < 8:
+        r = 0.0
+        for x in a:
+            r += x
+        return r
+    if n <= 128:
+        r = a[:8].copy()
+        m = n - (n % 8)
+        for i in range(8, m, 8):
+            r += a[i:i + 8]
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        for i in range(m, n):
+            res += a[i]
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return numpy_pairwise_sum(a[:n2]) + numpy_pairwise_sum(a[n2:])
+
+
 def kmeans_1d(values, k, seed=1, tol=1e-4, max_iter=300):
     """KMeans(n_clusters=k, random_state=seed).fit(values.reshape(-1, 1)) (_kmeans.py:1440-1563):
     returns (labels, cluster_centers_, n_iter_)."""

@@ -73,3 +73,15 @@ def test_library_random_stream_is_numpys():
             w = np.ones(n)
             assert _native.numpy_choice_uniform(seed, n) == \
                 np.random.RandomState(seed).choice(n, p=w / w.sum())
+
+
+def test_numpy_pairwise_sum_restatement_is_bit_exact():
+    """The order in which the quantiser sums its data mean on the GPU is NumPy's; this pins the
+    restatement of that order to the installed NumPy (np.add.reduce, ndarray.mean on the
+    [n, 1] layout KMeans sees) bit for bit, ragged sizes included."""
+    rng = np.random.RandomState(0)
+    for n in (1, 5, 8, 9, 100, 128, 129, 1000, 4097, 20000, 80000, 123457, 300001):
+        a = rng.rand(n) ** 2
+        want = np.add.reduce(a)
+        assert oracle.numpy_pairwise_sum(a) == want, n
+        assert a.reshape(-1, 1).mean(axis=0)[0] == want / n, n

@@ -1,11 +1,7 @@
 #!/bin/bash
+# scratch: the command list of the most recent gpurun call (overwritten per call).  The round-end
+# validation of the third session (profiles/r2_pytest_gpu_summary_session3.txt) was:
 mkdir -p gpurun_out
-timeout 60 python tools/bench_encode.py > gpurun_out/r2c51_bench_encode.txt 2>&1; head -3 gpurun_out/r2c51_bench_encode.txt | cut -c1-200; python - <<'P'
-import torch, time, sys, os
-sys.path.insert(0, os.getcwd())
-from graphrole_b200 import _native
-W = torch.rand(10_000_000, 8, device='cuda:0') ** 2
-q = _native.Quantizer(W.numel(), 'cuda:0')
-q.bind(W); torch.cuda.synchronize()
-t0 = time.perf_counter(); q.bind(W); torch.cuda.synchronize(); print('second bind ms', round((time.perf_counter() - t0) * 1e3, 2))
-P
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
