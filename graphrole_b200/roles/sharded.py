@@ -95,16 +95,42 @@ class CudaNmfBackend:
             pass
 
 
+def _all_ranks_agree(ok: bool, group, device) -> bool:
+    """True when `ok` holds on every rank (all-reduce MIN); every rank gets the same answer, so a
+    failure on one rank becomes an exception on all of them instead of a hang in the next
+    collective."""
+    if not dist.is_initialized():
+        return ok
+    if dist.get_backend(group) != 'nccl':
+        device = torch.device('cpu')
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 class RowShardedNmf:
-    """Multiplicative updates on this rank's rows; `fit` mirrors gr_nmf_mu_f32's loop."""
+    """Multiplicative updates on this rank's rows; `fit` mirrors gr_nmf_mu_f32's loop.
+    Construction is collective: every rank must hold at least one row and get its workspaces,
+    or all ranks raise."""
 
     def __init__(self, n_local: int, f: int, r: int, device=None, group=None, backend=None):
         self.n, self.f, self.r = int(n_local), int(f), int(r)
         self.group = group
+        device = torch.device('cpu') if backend is not None and device is None else (
+            torch.device('cuda', torch.cuda.current_device()) if device is None
+            else torch.device(device))
+        if not _all_ranks_agree(self.n >= 1, group, device):
+            raise ValueError('row-sharded NMF: a rank holds no rows (fewer row blocks than ranks)')
+        error = None
         if backend is None:
-            device = torch.device('cuda', torch.cuda.current_device()) if device is None \
-                else torch.device(device)
-            backend = CudaNmfBackend(self.n, self.f, self.r, device)
+            try:
+                backend = CudaNmfBackend(self.n, self.f, self.r, device)
+            except Exception as exc:           # e.g. out of memory on this rank only
+                error = exc
+        if not _all_ranks_agree(error is None, group, device):
+            if backend is not None and hasattr(backend, 'close'):
+                backend.close()
+            raise RuntimeError(f'row-sharded NMF: set-up failed on a rank ({error!r})')
         self.backend = backend
         self.allreduce_bytes_per_iteration = 4 * (self.r * self.f + self.r * self.r)
 

@@ -299,3 +299,27 @@ def test_row_shard_covers_all_rows_in_whole_blocks():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert all(lo % 128 == 0 for lo, _ in spans if lo < n)
+
+
+def _empty_shard_worker(rank, world, port, ret):
+    from graphrole_b200.roles.sharded import RowShardedNmf, row_shard
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        lo, hi = row_shard(130, world, rank)          # 128-row blocks: the third rank gets nothing
+        try:
+            RowShardedNmf(hi - lo, 8, 2, backend=_OracleNmfBackend())
+            ret[rank] = 'constructed'
+        except ValueError as exc:
+            ret[rank] = 'ValueError: ' + str(exc)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_nmf_refuses_an_empty_shard_on_every_rank():
+    """A rank without rows cannot create its workspaces; the refusal is voted on, so ALL ranks
+    raise instead of the healthy ones waiting in the first all-reduce."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_empty_shard_worker, args=(3, port, ret), nprocs=3, join=True)
+    assert all(ret[r].startswith('ValueError') for r in range(3)), dict(ret)
