@@ -292,9 +292,11 @@ int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* rowptr_dev,
  *     KMeans(n_clusters=n_bins, random_state=seed).fit(X.reshape(X.size, 1)); centres[labels]
  * (sklearn/cluster/_kmeans.py: fit :1440-1563, k-means++ :180-278, Lloyd :620-758).
  * gr_quantizer_bind_*   takes the matrix (rows x cols, row stride ld, row-major flattening order
- *     like X.reshape): centres the entries by their mean, sorts them once and prefix-sums the
- *     sorted values -- shared by every n_bins tried on the same matrix (the grid of
- *     roles/extract.py:121-133 quantises one factor with 2^1 .. 2^8 bins).
+ *     like X.reshape): centres the entries by their mean -- summed in NumPy's pairwise order, so
+ *     that it is X.mean() to the last bit (on grid-valued data the assignment of exactly
+ *     equidistant points depends on it) --, sorts them once (values and permutation) and
+ *     prefix-sums the sorted values -- shared by every n_bins tried on the same matrix (the grid
+ *     of roles/extract.py:121-133 quantises one factor with 2^1 .. 2^8 bins).
  * gr_quantizer_encode_* k-means++ seeding with NumPy's RandomState(seed) stream (the reference
  *     hard-codes seed 1), Lloyd iterations until labels repeat or the squared centre shift is
  *     <= tol * var(X) (sklearn: tol 1e-4, max_iter 300), then out = centre of every entry's
@@ -305,7 +307,7 @@ int gr_level0_features_f64(int64_t n, int64_t nnz, const int64_t* rowptr_dev,
  *     n_bins > rows * cols is refused with sklearn's message "n_samples=... should be >=
  *     n_clusters=..." (GR_ERR_INVALID_ARGUMENT): callers rely on it (roles/extract.py:127-129).
  *     n_bins <= 1024.  Labels equal scikit-learn's when the data hold >= n_bins distinct values.
- * The handle owns about 48 bytes of device workspace per entry of `capacity`.
+ * The handle owns about 50 bytes of device workspace per entry of `capacity`.
  */
 typedef struct gr_quantizer gr_quantizer_t;
 
