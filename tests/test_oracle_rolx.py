@@ -85,3 +85,80 @@ def test_numpy_pairwise_sum_restatement_is_bit_exact():
         want = np.add.reduce(a)
         assert oracle.numpy_pairwise_sum(a) == want, n
         assert a.reshape(-1, 1).mean(axis=0)[0] == want / n, n
+
+
+def _seeds_by_the_range_rule(x, k, rs):
+    """NumPy model of the seeding in csrc/rolx_epilogue.cu: a candidate is evaluated, and the
+    chosen centre applied, only on the SORTED range strictly between the chosen centres next to
+    it (none when its value is a centre already, everything when a neighbour is within the
+    rounding-noise guard); the sampling still sums the distances in the original order."""
+    import bisect
+    n = x.size
+    order = np.argsort(x, kind='stable')
+    xs = x[order]
+    guard = 1e-14 * max(xs[0] ** 2, xs[-1] ** 2)
+    trials = 2 + int(np.log(k))
+
+    def sqd(c, v):
+        return np.maximum((-2.0 * (c * v) + c * c) + v * v, 0)
+
+    idx = np.full(k, -1, dtype=np.int64)
+    idx[0] = rs.choice(n, p=np.ones(n) / n)
+    closest = sqd(x[idx[0]], x)
+    centres = [x[idx[0]]]
+    for c in range(1, k):
+        pot = closest.sum()
+        cand = np.searchsorted(np.cumsum(closest), rs.uniform(size=trials) * pot)
+        np.clip(cand, None, n - 1, out=cand)
+        pots, ranges = [], []
+        for j in cand:
+            cv = x[j]
+            pos = bisect.bisect_left(centres, cv)
+            if pos < len(centres) and centres[pos] == cv:
+                ranges.append((0, 0))
+                pots.append(pot)
+                continue
+            c_lo = centres[pos - 1] if pos > 0 else None
+            c_hi = centres[pos] if pos < len(centres) else None
+            everything = (c_lo is not None and (cv - c_lo) ** 2 <= guard) or \
+                         (c_hi is not None and (c_hi - cv) ** 2 <= guard)
+            lo = 0 if (everything or c_lo is None) else int(np.searchsorted(xs, c_lo, 'right'))
+            hi = n if (everything or c_hi is None) else int(np.searchsorted(xs, c_hi, 'left'))
+            ranges.append((lo, hi))
+            cl = closest[order[lo:hi]]
+            pots.append(pot - np.sum(cl - np.minimum(cl, sqd(cv, xs[lo:hi]))))
+        best = int(np.argmin(pots))
+        lo, hi = ranges[best]
+        cv = x[cand[best]]
+        sel = order[lo:hi]
+        closest[sel] = np.minimum(closest[sel], sqd(cv, xs[lo:hi]))
+        idx[c] = cand[best]
+        bisect.insort(centres, cv)
+    return idx
+
+
+@pytest.mark.parametrize('kind', ['uniform', 'integers', 'skewed', 'near_duplicates',
+                                  'two_decimals', 'zero_mass'])
+def test_range_rule_of_the_incremental_seeding_reproduces_kmeans_plusplus(kind):
+    """The rule the CUDA seeding relies on -- a new centre only changes distances between the
+    chosen centres next to it -- gives the centres of the full evaluation (the restatement of
+    sklearn's _kmeans_plusplus above), sklearn's rounded distance formula included.  Compared by
+    value: among candidates of EQUAL value the full evaluation's argmin is decided by BLAS
+    rounding noise in NumPy itself.  Cases with fewer distinct values than centres are the
+    degenerate regime the library handles separately."""
+    rng = np.random.RandomState(len(kind))
+    for n in (50, 500, 4000):
+        v = {'uniform': lambda: rng.rand(n),
+             'integers': lambda: rng.randint(0, 40, n).astype(float),
+             'skewed': lambda: rng.rand(n) ** 4,
+             'near_duplicates': lambda: np.concatenate([rng.rand(n // 2) * 1e-9 + 0.5,
+                                                        rng.rand(n - n // 2)]),
+             'two_decimals': lambda: np.round(rng.rand(n), 2),
+             'zero_mass': lambda: np.abs(rng.randn(n)) * (rng.rand(n) < 0.3)}[kind]()
+        x = v - v.mean()
+        for k in (2, 4, 16, 32):
+            if k > min(n, np.unique(v).size):
+                continue
+            want = oracle.kmeans_plusplus_1d(x, k, np.random.RandomState(1 + n))
+            got = _seeds_by_the_range_rule(x, k, np.random.RandomState(1 + n))
+            np.testing.assert_array_equal(x[got], x[want], err_msg=f'{kind} n={n} k={k}')
