@@ -69,3 +69,30 @@ def test_nndsvda_from_exact_svd_matches_sklearn_on_well_separated_spectrum():
     W, H = oracle.nndsvda_from_svd(X, U, S, Vt)
     np.testing.assert_allclose(W, W_ref, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(H, H_ref, rtol=1e-6, atol=1e-8)
+
+
+def test_zero_padding_is_a_fixed_point_of_the_updates():
+    """What lets every rank and every feature count run the tensor-core kernels: a zero column of
+    W with the matching zero row of H (rank padded to a multiple of 4 inside the library), and a
+    zero column of X with the matching zero column of H0 (feature count padded by
+    roles.factor.FeatureMatrix), stay zero under the multiplicative updates and leave the real
+    entries what they were."""
+    rng = np.random.RandomState(2)
+    n, f, r = 200, 30, 5
+    X = rng.rand(n, 4) @ rng.rand(4, f) + 0.05 * rng.rand(n, f)
+    W0, H0 = rng.rand(n, r) + 0.1, rng.rand(r, f) + 0.1
+    W, H, it = oracle.fit_multiplicative_update(X, W0, H0, max_iter=60, tol=0)
+    # rank 5 -> 8
+    Wp, Hp, _ = oracle.fit_multiplicative_update(
+        X, np.pad(W0, ((0, 0), (0, 3))), np.pad(H0, ((0, 3), (0, 0))), max_iter=60, tol=0)
+    assert not Wp[:, r:].any() and not Hp[r:].any()
+    np.testing.assert_allclose(Wp[:, :r], W, rtol=1e-10)
+    np.testing.assert_allclose(Hp[:r], H, rtol=1e-10)
+    # 30 features -> 32
+    Wq, Hq, _ = oracle.fit_multiplicative_update(
+        np.pad(X, ((0, 0), (0, 2))), W0, np.pad(H0, ((0, 0), (0, 2))), max_iter=60, tol=0)
+    assert not Hq[:, f:].any()
+    np.testing.assert_allclose(Wq, W, rtol=1e-10)
+    np.testing.assert_allclose(Hq[:, :f], H, rtol=1e-10)
+    assert oracle.frobenius_error(np.pad(X, ((0, 0), (0, 2))), Wq, Hq) == pytest.approx(
+        oracle.frobenius_error(X, W, H), rel=1e-12)
