@@ -96,3 +96,31 @@ def test_zero_padding_is_a_fixed_point_of_the_updates():
     np.testing.assert_allclose(Hq[:, :f], H, rtol=1e-10)
     assert oracle.frobenius_error(np.pad(X, ((0, 0), (0, 2))), Wq, Hq) == pytest.approx(
         oracle.frobenius_error(X, W, H), rel=1e-12)
+
+
+def _tf32(a):
+    """float32 values rounded to TF32 (10 mantissa bits, nearest, ties away like cvt.rna)."""
+    u = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return u.view(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize('n,f,r', [(1, 4, 4), (127, 32, 4), (300, 64, 4), (1000, 132, 20),
+                                   (5003, 96, 12), (257, 512, 32)])
+def test_tf32_operand_rounding_moves_the_error_within_the_stated_bound(n, f, r):
+    """A NumPy model of the tensor-core convergence check (W and H rounded to TF32, everything
+    else exact) against the float64 error: the difference stays inside the bound the GPU test
+    states (tests/test_nmf_gpu.py::tf32_error_bound: 1e-5 relative + 3 dn / sqrt(r (n + f)) +
+    dn^2 / (2 err) with dn = 2^-11 ||W H||_F), on random factors and on a fitted model."""
+    rng = np.random.RandomState(n % 89 + f + r)
+    X, W, H = (rng.rand(n, f).astype(np.float32).astype(np.float64),
+               rng.rand(n, r).astype(np.float32).astype(np.float64),
+               rng.rand(r, f).astype(np.float32).astype(np.float64))
+    Wf, Hf, _ = oracle.fit_multiplicative_update(X, W, H, max_iter=30, tol=0)
+    for Wc, Hc in ((W, H), (Wf.astype(np.float32).astype(np.float64),
+                            Hf.astype(np.float32).astype(np.float64))):
+        want = oracle.frobenius_error(X, Wc, Hc)
+        got = oracle.frobenius_error(X, _tf32(Wc), _tf32(Hc))
+        dn = 2.0 ** -11 * np.linalg.norm(Wc @ Hc)
+        bound = 1e-5 * want + 3 * dn / np.sqrt(r * (n + f)) + dn * dn / (2 * want)
+        assert abs(got - want) <= bound, (abs(got - want), bound)
